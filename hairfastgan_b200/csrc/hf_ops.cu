@@ -1,0 +1,553 @@
+// HBM-bound SIMT kernels of the hot path: upfirdn2d, fused bias+activation, style affine /
+// demodulation tables, NCHW->NHWC modulate+cast pre-pass, RGB combine (+ up-FIR of the skip),
+// standalone ToRGB, weight packing.  All fp32 math; 16-bit only as storage for tensor-core operands.
+#include "hf_kernels.cuh"
+
+namespace hf {
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// =============================================================================================
+// upfirdn2d  (reference semantics: models/stylegan2/op/upfirdn2d.py:159-200,
+//             op/upfirdn2d_kernel.cu:107-207 -- zero-stuff, pad/crop, convolve (flipped taps), decimate)
+// =============================================================================================
+
+// Fast path: up = 1, 4x4 taps, down in {1,2}.  One CTA = one (plane, 32x64 | 16x64 output tile);
+// the input window is staged once in shared memory with coalesced row loads, each thread produces
+// 4 consecutive outputs per row from a sliding register window and stores them as one float4.
+template <int DOWN, int ROWS>
+__global__ void __launch_bounds__(256) upfirdn2d_up1_k4_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                               const float* __restrict__ k, int in_h, int in_w,
+                                                               int out_h, int out_w, int px0, int py0) {
+  constexpr int TW = 64;
+  constexpr int IN_ROWS = (ROWS - 1) * DOWN + 4;
+  constexpr int IN_COLS = (TW - 1) * DOWN + 4;
+  constexpr int PITCH = IN_COLS + 1;
+  __shared__ float tile[IN_ROWS * PITCH];
+  __shared__ float kf[16];
+  const int plane = blockIdx.z;
+  const int oy0 = blockIdx.y * ROWS, ox0 = blockIdx.x * TW;
+  const float* xp = x + (size_t)plane * in_h * in_w;
+  if (threadIdx.x < 16) kf[threadIdx.x] = k[15 - threadIdx.x];   // flipped: kf[ky][kx] = k[3-ky][3-kx]
+  const int gy0 = oy0 * DOWN - py0, gx0 = ox0 * DOWN - px0;
+  for (int i = threadIdx.x; i < IN_ROWS * IN_COLS; i += 256) {
+    int r = i / IN_COLS, c = i - r * IN_COLS;
+    int gy = gy0 + r, gx = gx0 + c;
+    float v = 0.f;
+    if (gy >= 0 && gy < in_h && gx >= 0 && gx < in_w) v = __ldg(xp + (size_t)gy * in_w + gx);
+    tile[r * PITCH + c] = v;
+  }
+  __syncthreads();
+  float kr[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kr[i] = kf[i];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads
+  float* yp = y + (size_t)plane * out_h * out_w;
+#pragma unroll
+  for (int rr = 0; rr < ROWS / 16; ++rr) {
+    const int r = ty + rr * 16;
+    const int oy = oy0 + r, ox = ox0 + tx * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const float* row = tile + (r * DOWN + ky) * PITCH + tx * 4 * DOWN;
+      float w[3 * DOWN + 4];
+#pragma unroll
+      for (int i = 0; i < 3 * DOWN + 4; ++i) w[i] = row[i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx) acc[j] = fmaf(w[j * DOWN + kx], kr[ky * 4 + kx], acc[j]);
+    }
+    if (oy < out_h) {
+      float* dst = yp + (size_t)oy * out_w + ox;
+      if (ox + 3 < out_w && ((out_w & 3) == 0)) {
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (ox + j < out_w) dst[j] = acc[j];
+      }
+    }
+  }
+}
+
+// Fast path: up = 2, down = 1, 4x4 taps (the RGB-skip Upsample, model.py:35-53).  Only 2x2 of the
+// 16 taps hit a non-zero sample; each thread makes 4 consecutive outputs of one row.
+__global__ void __launch_bounds__(256) upfirdn2d_up2_k4_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                               const float* __restrict__ k, int in_h, int in_w,
+                                                               int out_h, int out_w, int px0, int py0,
+                                                               int64_t total_quads) {
+  __shared__ float kf[16];
+  if (threadIdx.x < 16) kf[threadIdx.x] = k[15 - threadIdx.x];
+  __syncthreads();
+  const int quads_per_row = (out_w + 3) >> 2;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total_quads;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    int qx = (int)(q % quads_per_row);
+    int64_t t = q / quads_per_row;
+    int oy = (int)(t % out_h);
+    int plane = (int)(t / out_h);
+    const float* xp = x + (size_t)plane * in_h * in_w;
+    const int ky0 = (py0 - oy) & 1;          // oy + ky - py0 must be even
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int ky = ky0 + 2 * a;
+      const int uy = oy + ky - py0;
+      const int iy = uy >> 1;
+      if (uy < 0 || iy >= in_h) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ox = qx * 4 + j;
+        const int kx0 = (px0 - ox) & 1;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int kx = kx0 + 2 * b;
+          const int ux = ox + kx - px0;
+          const int ix = ux >> 1;
+          if (ux >= 0 && ix < in_w) acc[j] = fmaf(__ldg(xp + (size_t)iy * in_w + ix), kf[ky * 4 + kx], acc[j]);
+        }
+      }
+    }
+    float* dst = y + ((size_t)plane * out_h + oy) * out_w + qx * 4;
+    if ((out_w & 3) == 0) {
+      *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {
+      for (int j = 0; j < 4; ++j)
+        if (qx * 4 + j < out_w) dst[j] = acc[j];
+    }
+  }
+}
+
+// General path: any up/down/pad (incl. negative pads = crop) and any kernel size.
+__global__ void __launch_bounds__(256) upfirdn2d_general_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                const float* __restrict__ k, int in_h, int in_w,
+                                                                int out_h, int out_w, int kh, int kw, int up_x,
+                                                                int up_y, int down_x, int down_y, int px0, int py0,
+                                                                int64_t total) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int ox = (int)(idx % out_w);
+    int64_t t = idx / out_w;
+    int oy = (int)(t % out_h);
+    int plane = (int)(t / out_h);
+    const float* xp = x + (size_t)plane * in_h * in_w;
+    float acc = 0.f;
+    for (int ky = 0; ky < kh; ++ky) {
+      int uy = oy * down_y + ky - py0;          // coordinate in the zero-stuffed image
+      if (uy < 0 || uy % up_y != 0) continue;
+      int iy = uy / up_y;
+      if (iy >= in_h) continue;
+      for (int kx = 0; kx < kw; ++kx) {
+        int ux = ox * down_x + kx - px0;
+        if (ux < 0 || ux % up_x != 0) continue;
+        int ix = ux / up_x;
+        if (ix >= in_w) continue;
+        acc = fmaf(__ldg(xp + (size_t)iy * in_w + ix), __ldg(k + (kh - 1 - ky) * kw + (kw - 1 - kx)), acc);
+      }
+    }
+    y[idx] = acc;
+  }
+}
+
+int launch_upfirdn2d(const float* x, float* y, const float* k, int planes, int in_h, int in_w, int kh, int kw,
+                     int up_x, int up_y, int down_x, int down_y, int px0, int px1, int py0, int py1,
+                     cudaStream_t st) {
+  HF_REQUIRE(x && y && k, "upfirdn2d: null pointer");
+  HF_REQUIRE(planes >= 0 && in_h > 0 && in_w > 0 && kh > 0 && kw > 0, "upfirdn2d: bad shape");
+  HF_REQUIRE(up_x > 0 && up_y > 0 && down_x > 0 && down_y > 0, "upfirdn2d: up/down must be positive");
+  const int out_h = (in_h * up_y + py0 + py1 - kh) / down_y + 1;
+  const int out_w = (in_w * up_x + px0 + px1 - kw) / down_x + 1;
+  HF_REQUIRE(in_h * up_y + py0 + py1 - kh >= 0 && in_w * up_x + px0 + px1 - kw >= 0,
+             "upfirdn2d: output would be empty (in %dx%d up %d pad %d,%d k %d)", in_h, in_w, up_y, py0, py1, kh);
+  if (planes == 0) return HF_OK;
+  const bool k4 = (kh == 4 && kw == 4);
+  const bool sym = (up_x == up_y && down_x == down_y);
+  if (k4 && sym && up_x == 1 && (down_x == 1 || down_x == 2) && planes <= 65535) {
+    if (down_x == 1) {
+      dim3 grid(cdiv(out_w, 64), cdiv(out_h, 32), planes);
+      upfirdn2d_up1_k4_kernel<1, 32><<<grid, 256, 0, st>>>(x, y, k, in_h, in_w, out_h, out_w, px0, py0);
+    } else {
+      dim3 grid(cdiv(out_w, 64), cdiv(out_h, 16), planes);
+      upfirdn2d_up1_k4_kernel<2, 16><<<grid, 256, 0, st>>>(x, y, k, in_h, in_w, out_h, out_w, px0, py0);
+    }
+  } else if (k4 && sym && up_x == 2 && down_x == 1) {
+    int64_t quads = (int64_t)planes * out_h * ((out_w + 3) / 4);
+    int grid = (int)std::min<int64_t>((quads + 255) / 256, (int64_t)num_sms() * 16);
+    upfirdn2d_up2_k4_kernel<<<grid, 256, 0, st>>>(x, y, k, in_h, in_w, out_h, out_w, px0, py0, quads);
+  } else {
+    int64_t total = (int64_t)planes * out_h * out_w;
+    int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
+    upfirdn2d_general_kernel<<<grid, 256, 0, st>>>(x, y, k, in_h, in_w, out_h, out_w, kh, kw, up_x, up_y,
+                                                    down_x, down_y, px0, py0, total);
+  }
+  HF_LAUNCH_OK("upfirdn2d");
+  count_launch();
+  return HF_OK;
+}
+
+// =============================================================================================
+// fused bias + activation  (op/fused_bias_act_kernel.cu:19-49, forward, act in {1 linear, 3 lrelu})
+// =============================================================================================
+template <bool VEC>
+__global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__ x, const float* __restrict__ b,
+                                                       float* __restrict__ y, int64_t n, int size_b,
+                                                       int64_t step_b, int act, float alpha, float scale) {
+  if (VEC) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+      float bb = size_b ? __ldg(b + ((i * 4) / step_b) % size_b) : 0.f;   // step_b % 4 == 0: one channel
+      float r[4] = {v.x + bb, v.y + bb, v.z + bb, v.w + bb};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float t = r[j];
+        if (act == 3) t = (t > 0.f) ? t : t * alpha;
+        r[j] = t * scale;
+      }
+      reinterpret_cast<float4*>(y)[i] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+  } else {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      float t = x[i];
+      if (size_b) t += __ldg(b + (i / step_b) % size_b);
+      if (act == 3) t = (t > 0.f) ? t : t * alpha;
+      y[i] = t * scale;
+    }
+  }
+}
+
+int launch_bias_act(const float* x, const float* b, float* y, int64_t n, int size_b, int64_t step_b, int act,
+                    float alpha, float scale, cudaStream_t st) {
+  HF_REQUIRE(x && y, "bias_act: null pointer");
+  HF_REQUIRE(act == 1 || act == 3, "bias_act: act must be 1 (linear) or 3 (leaky relu), got %d", act);
+  HF_REQUIRE(n >= 0 && size_b >= 0 && step_b >= 1, "bias_act: bad sizes");
+  HF_REQUIRE(size_b == 0 || b, "bias_act: bias pointer is null");
+  if (n == 0) return HF_OK;
+  const bool vec = (step_b % 4 == 0) && (n % 4 == 0) && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0);
+  int64_t work = vec ? n / 4 : n;
+  int grid = (int)std::min<int64_t>((work + 255) / 256, (int64_t)num_sms() * 16);
+  if (vec)
+    bias_act_kernel<true><<<grid, 256, 0, st>>>(x, b, y, n, size_b, step_b, act, alpha, scale);
+  else
+    bias_act_kernel<false><<<grid, 256, 0, st>>>(x, b, y, n, size_b, step_b, act, alpha, scale);
+  HF_LAUNCH_OK("bias_act");
+  count_launch();
+  return HF_OK;
+}
+
+// =============================================================================================
+// style affine (EqualLinear modulation, model.py:153-163 with bias_init=1) and demodulation table
+// =============================================================================================
+struct AffineJobs { AffineJob j[kMaxJobs]; int n; };
+struct DemodJobs { DemodJob j[kMaxJobs]; int n; };
+
+// One warp per output row i of one job; lanes split the D-long dot product (float4 loads).
+__global__ void __launch_bounds__(256) affine_kernel(const __grid_constant__ AffineJobs jobs, int B, int D,
+                                                     int64_t style_stride) {
+  int jb = 0;
+  while (jb + 1 < jobs.n && (int)blockIdx.x >= jobs.j[jb + 1].block_begin) ++jb;
+  const AffineJob& job = jobs.j[jb];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = ((int)blockIdx.x - job.block_begin) * 8 + warp;
+  if (i >= job.C) return;
+  const float* wrow = job.mw + (size_t)i * D;
+  const float mb = __ldg(job.mb + i);
+  for (int b = 0; b < B; ++b) {
+    const float* srow = job.style + (size_t)b * style_stride;
+    float acc = 0.f;
+    for (int j = lane * 4; j < D; j += 128) {
+      float4 w = __ldg(reinterpret_cast<const float4*>(wrow + j));
+      float4 s = __ldg(reinterpret_cast<const float4*>(srow + j));
+      acc = fmaf(w.x, s.x, acc); acc = fmaf(w.y, s.y, acc); acc = fmaf(w.z, s.z, acc); acc = fmaf(w.w, s.w, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) job.s[(size_t)b * job.C + i] = fmaf(acc, job.wscale, mb);
+  }
+}
+
+__global__ void __launch_bounds__(256) demod_kernel(const __grid_constant__ DemodJobs jobs, int B) {
+  int jb = 0;
+  while (jb + 1 < jobs.n && (int)blockIdx.x >= jobs.j[jb + 1].block_begin) ++jb;
+  const DemodJob& job = jobs.j[jb];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = ((int)blockIdx.x - job.block_begin) * 8 + warp;
+  if (o >= job.Cout) return;
+  const float* wrow = job.wsq + (size_t)o * job.Cin;
+  for (int b = 0; b < B; ++b) {
+    const float* srow = job.s + (size_t)b * job.Cin;
+    float acc = 0.f;
+    for (int i = lane; i < job.Cin; i += 32) {
+      float s = __ldg(srow + i);
+      acc = fmaf(s * s, __ldg(wrow + i), acc);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) job.d[(size_t)b * job.Cout + o] = rsqrtf(acc + 1e-8f);
+  }
+}
+
+int launch_affine(AffineJob* jobs, int njobs, int B, int D, int64_t style_stride, cudaStream_t st) {
+  HF_REQUIRE(njobs > 0 && njobs <= kMaxJobs, "affine: bad job count %d", njobs);
+  HF_REQUIRE(D % 4 == 0 && style_stride % 4 == 0, "affine: style_dim and stride must be multiples of 4");
+  AffineJobs aj;
+  aj.n = njobs;
+  int blocks = 0;
+  for (int i = 0; i < njobs; ++i) {
+    jobs[i].block_begin = blocks;
+    blocks += cdiv(jobs[i].C, 8);
+    aj.j[i] = jobs[i];
+  }
+  affine_kernel<<<blocks, 256, 0, st>>>(aj, B, D, style_stride);
+  HF_LAUNCH_OK("affine");
+  count_launch();
+  return HF_OK;
+}
+
+int launch_demod(DemodJob* jobs, int njobs, int B, cudaStream_t st) {
+  HF_REQUIRE(njobs > 0 && njobs <= kMaxJobs, "demod: bad job count %d", njobs);
+  DemodJobs dj;
+  dj.n = njobs;
+  int blocks = 0;
+  for (int i = 0; i < njobs; ++i) {
+    jobs[i].block_begin = blocks;
+    blocks += cdiv(jobs[i].Cout, 8);
+    dj.j[i] = jobs[i];
+  }
+  demod_kernel<<<blocks, 256, 0, st>>>(dj, B);
+  HF_LAUNCH_OK("demod");
+  count_launch();
+  return HF_OK;
+}
+
+// =============================================================================================
+// pre-pass: NCHW fp32 -> NHWC 16-bit with the per-(b,cin) style scale folded in
+// (the "x * s" of y = d * conv(x*s, W~)); optional FSE feature blend.
+// =============================================================================================
+template <int DT>
+__global__ void __launch_bounds__(256) modulate_to_nhwc_kernel(const float* __restrict__ x, int64_t x_bstride,
+                                                               const float* __restrict__ s,
+                                                               const float* __restrict__ feat, float alpha,
+                                                               uint16_t* __restrict__ xh, int C, int HW) {
+  __shared__ float tile[64][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* xb = x + (size_t)b * x_bstride;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int c = c0 + ty + 8 * k, p = p0 + tx;
+    float v = 0.f;
+    if (c < C && p < HW) {
+      v = __ldg(xb + (size_t)c * HW + p);
+      if (feat) v = (1.f - alpha) * v + alpha * __ldg(feat + ((size_t)b * C + c) * HW + p);
+      v *= __ldg(s + (size_t)b * C + c);
+    }
+    tile[ty + 8 * k][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int p = p0 + ty + 8 * k, c = c0 + 2 * tx;
+    if (p < HW && c < C) {
+      uint32_t packed = Half2T<DT>::pack(tile[2 * tx][ty + 8 * k], tile[2 * tx + 1][ty + 8 * k]);
+      *reinterpret_cast<uint32_t*>(xh + ((size_t)b * HW + p) * C + c) = packed;
+    }
+  }
+}
+
+int launch_modulate_to_nhwc(const float* x, int x_broadcast, const float* s, const float* feat, float alpha,
+                            void* xh, int B, int C, int HW, int dtype, cudaStream_t st) {
+  HF_REQUIRE(x && s && xh, "modulate_to_nhwc: null pointer");
+  HF_REQUIRE(C % 2 == 0, "modulate_to_nhwc: C must be even");
+  dim3 grid(cdiv(HW, 32), cdiv(C, 64), B);
+  int64_t bstride = x_broadcast ? 0 : (int64_t)C * HW;
+  if (dtype == HF_BF16)
+    modulate_to_nhwc_kernel<HF_BF16><<<grid, 256, 0, st>>>(x, bstride, s, feat, alpha, (uint16_t*)xh, C, HW);
+  else
+    modulate_to_nhwc_kernel<HF_F16><<<grid, 256, 0, st>>>(x, bstride, s, feat, alpha, (uint16_t*)xh, C, HW);
+  HF_LAUNCH_OK("modulate_to_nhwc");
+  count_launch();
+  return HF_OK;
+}
+
+// =============================================================================================
+// RGB combine: bias + ordered sum of the per-N-tile ToRGB partials + Upsample(skip)
+// (ToRGB.forward model.py:356-365; Upsample = upfirdn2d(up=2, pad=(2,1)), model.py:35-53)
+// =============================================================================================
+__global__ void __launch_bounds__(256) rgb_combine_kernel(const float* partial, int num_partials,
+                                                          int64_t partial_stride, const float* __restrict__ bias,
+                                                          const float* __restrict__ skip,
+                                                          const float* __restrict__ upk, float* rgb,
+                                                          int H, int W, int64_t total) {
+  __shared__ float kf[16];
+  if (threadIdx.x < 16) kf[threadIdx.x] = upk ? upk[15 - threadIdx.x] : 0.f;
+  __syncthreads();
+  const int h2 = H >> 1, w2 = W >> 1;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int X = (int)(idx % W);
+    int64_t t = idx / W;
+    int Y = (int)(t % H);
+    int plane = (int)(t / H);            // b*3 + j
+    float acc = bias ? __ldg(bias + plane % 3) : 0.f;
+    for (int q = 0; q < num_partials; ++q) acc += partial[q * partial_stride + idx];   // may alias rgb (in place)
+    if (skip) {
+      const float* sp = skip + (size_t)plane * h2 * w2;
+      const int ky0 = Y & 1, kx0 = X & 1;      // pad0 = 2: Y + ky - 2 even
+      float up = 0.f;
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        int ky = ky0 + 2 * a;
+        int uy = Y + ky - 2;
+        int iy = uy >> 1;
+        if (uy < 0 || iy >= h2) continue;
+#pragma unroll
+        for (int bq = 0; bq < 2; ++bq) {
+          int kx = kx0 + 2 * bq;
+          int ux = X + kx - 2;
+          int ix = ux >> 1;
+          if (ux >= 0 && ix < w2) up = fmaf(__ldg(sp + (size_t)iy * w2 + ix), kf[ky * 4 + kx], up);
+        }
+      }
+      acc += up;
+    }
+    rgb[idx] = acc;
+  }
+}
+
+int launch_rgb_combine(const float* partial, int num_partials, const float* bias, const float* skip,
+                       const float* up_kernel, float* rgb, int B, int H, int W, cudaStream_t st) {
+  HF_REQUIRE(rgb && (partial || num_partials == 0), "rgb_combine: null pointer");
+  HF_REQUIRE(!skip || up_kernel, "rgb_combine: skip given without an upsample kernel");
+  int64_t total = (int64_t)B * 3 * H * W;
+  int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
+  rgb_combine_kernel<<<grid, 256, 0, st>>>(partial, num_partials, total, bias, skip, up_kernel, rgb, H, W, total);
+  HF_LAUNCH_OK("rgb_combine");
+  count_launch();
+  return HF_OK;
+}
+
+// =============================================================================================
+// standalone ToRGB on an fp32 NCHW feature map (module-level API): one pass over x
+// =============================================================================================
+__global__ void __launch_bounds__(256) torgb_nchw_kernel(const float* __restrict__ x, const float* __restrict__ w1,
+                                                         float w_scale, const float* __restrict__ s,
+                                                         float* __restrict__ part, int C, int HW) {
+  extern __shared__ float ws[];      // [3][C] = w1[j,i] * scale * s[b,i]
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 3 * C; i += 256) {
+    int c = i % C;
+    ws[i] = __ldg(w1 + i) * w_scale * __ldg(s + (size_t)b * C + c);
+  }
+  __syncthreads();
+  const float* xb = x + (size_t)b * C * HW;
+  for (int p = blockIdx.x * 256 + threadIdx.x; p < HW; p += gridDim.x * 256) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < C; ++c) {
+      float v = __ldg(xb + (size_t)c * HW + p);
+      a0 = fmaf(v, ws[c], a0);
+      a1 = fmaf(v, ws[C + c], a1);
+      a2 = fmaf(v, ws[2 * C + c], a2);
+    }
+    float* pb = part + (size_t)b * 3 * HW;
+    pb[p] = a0; pb[HW + p] = a1; pb[2 * (size_t)HW + p] = a2;
+  }
+}
+
+int launch_torgb_nchw(const float* x, const float* w1, float w_scale, const float* s, const float* bias,
+                      const float* skip, const float* up_kernel, float* y, int B, int C, int H, int W,
+                      cudaStream_t st) {
+  HF_REQUIRE(x && w1 && s && y, "torgb: null pointer");
+  HF_REQUIRE(3 * C * sizeof(float) <= 48 * 1024, "torgb: too many channels (%d)", C);
+  const int HW = H * W;
+  dim3 grid(std::min(cdiv(HW, 256), num_sms() * 4), B);
+  // y doubles as the partial buffer; rgb_combine then adds bias + upsampled skip in place.
+  torgb_nchw_kernel<<<grid, 256, 3 * C * sizeof(float), st>>>(x, w1, w_scale, s, y, C, HW);
+  HF_LAUNCH_OK("torgb_nchw");
+  count_launch();
+  return launch_rgb_combine(y, 1, bias, skip, up_kernel, y, B, H, W, st);
+}
+
+// =============================================================================================
+// weight packing (once per weight load)
+// =============================================================================================
+// plain: wpk[o][tap*Cin + c] = W[o,c,dy,dx] * scale (tap = dy*3+dx, correlation form of F.conv2d)
+// up   : the stride-2 transposed conv (model.py:260) composed with the 4x4 blur (pad (1,1), model.py:263)
+//        as four 3x3 correlations, one per output parity (py,px); N row = (o/32)*128 + (py*2+px)*32 + o%32
+//        Kp[py,px][dy,dx] = sum_{a,b} W[a,b] * blur[2-a+u, 2-b+v],  u = py+2-2dy, v = px+2-2dx
+template <int DT>
+__global__ void __launch_bounds__(256) pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ blur,
+                                                        uint16_t* __restrict__ wpk, float* __restrict__ wsq,
+                                                        int Cout, int Cin, int ksize, int up, float scale) {
+  const int taps = ksize * ksize;
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)Cout * Cin) return;
+  const int c = (int)(idx % Cin), o = (int)(idx / Cin);
+  float wv[9];
+  float sq = 0.f;
+  for (int t = 0; t < taps; ++t) {
+    wv[t] = w[((size_t)o * Cin + c) * taps + t] * scale;
+    sq = fmaf(wv[t], wv[t], sq);
+  }
+  if (wsq) wsq[idx] = sq;
+  const size_t K = (size_t)taps * Cin;
+  if (!up) {
+    for (int t = 0; t < taps; ++t) wpk[(size_t)o * K + (size_t)t * Cin + c] = Half2T<DT>::one(wv[t]);
+  } else {
+    float bk[16];
+    for (int i = 0; i < 16; ++i) bk[i] = blur[i];
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const size_t row = (size_t)(o / 32) * 128 + (size_t)(py * 2 + px) * 32 + (o % 32);
+        for (int dy = 0; dy < 3; ++dy)
+          for (int dx = 0; dx < 3; ++dx) {
+            const int u = py + 2 - 2 * dy, v = px + 2 - 2 * dx;
+            float acc = 0.f;
+            for (int a = 0; a < 3; ++a)
+              for (int b = 0; b < 3; ++b) {
+                int iy = 2 - a + u, ix = 2 - b + v;
+                if (iy >= 0 && iy < 4 && ix >= 0 && ix < 4) acc = fmaf(wv[a * 3 + b], bk[iy * 4 + ix], acc);
+              }
+            wpk[row * K + (size_t)(dy * 3 + dx) * Cin + c] = Half2T<DT>::one(acc);
+          }
+      }
+  }
+}
+
+int launch_pack_conv(const float* w, const float* blur, void* wpk, float* wsq, int Cout, int Cin, int ksize,
+                     int up, int nc, int dtype, cudaStream_t st) {
+  (void)nc;
+  HF_REQUIRE(w && wpk, "pack_conv: null pointer");
+  HF_REQUIRE(ksize == 3 || ksize == 1, "pack_conv: kernel size %d unsupported", ksize);
+  HF_REQUIRE(!up || (ksize == 3 && blur && Cout % 32 == 0), "pack_conv: upsample needs 3x3, blur kernel, Cout%%32==0");
+  const float scale = 1.0f / sqrtf((float)(Cin * ksize * ksize));
+  int64_t total = (int64_t)Cout * Cin;
+  int grid = cdiv(total, 256);
+  if (dtype == HF_BF16)
+    pack_conv_kernel<HF_BF16><<<grid, 256, 0, st>>>(w, blur, (uint16_t*)wpk, wsq, Cout, Cin, ksize, up, scale);
+  else
+    pack_conv_kernel<HF_F16><<<grid, 256, 0, st>>>(w, blur, (uint16_t*)wpk, wsq, Cout, Cin, ksize, up, scale);
+  HF_LAUNCH_OK("pack_conv");
+  count_launch();
+  return HF_OK;
+}
+
+__global__ void scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n, float scale) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src[i] * scale;
+}
+int launch_scale_copy(const float* src, float* dst, int64_t n, float scale, cudaStream_t st) {
+  HF_REQUIRE(src && dst, "scale_copy: null pointer");
+  if (n == 0) return HF_OK;
+  int grid = (int)std::min<int64_t>((n + 255) / 256, 4096);
+  scale_copy_kernel<<<grid, 256, 0, st>>>(src, dst, n, scale);
+  HF_LAUNCH_OK("scale_copy");
+  count_launch();
+  return HF_OK;
+}
+
+}  // namespace hf

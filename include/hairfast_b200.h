@@ -1,0 +1,182 @@
+/* hairfast_b200.h -- C ABI of libhairfast_sm100.so
+ *
+ * B200 (sm_100a) implementation of the HairFastGAN hot path: the StyleGAN2 generator forward
+ * (ModulatedConv2d / StyledConv / ToRGB / upfirdn2d / fused bias+LeakyReLU).  Plain pointers and
+ * sizes only -- no torch types.  All pointers are DEVICE pointers unless stated otherwise; every
+ * output buffer is caller-allocated (the library never allocates device memory); every call
+ * enqueues on the given cudaStream_t (passed as void*) and returns without synchronising, so the
+ * calls are CUDA-graph capturable.  Return value: HF_OK (0) or a negative error code;
+ * hf_last_error() gives the message (thread-local).
+ *
+ * Each entry point cites the reference interface (AIRI-Institute/HairFastGAN @ 49e98019) it
+ * replaces.  INTEGRATION.md shows the reference-side binding.
+ */
+#ifndef HAIRFAST_B200_H_
+#define HAIRFAST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HF_OK 0
+#define HF_ERR_INVALID (-1)     /* bad argument / unsupported shape */
+#define HF_ERR_CUDA (-2)        /* CUDA runtime / driver error */
+#define HF_ERR_UNSUPPORTED (-3) /* device is not sm_100 */
+
+/* 16-bit storage/operand type of the tensor-core path (accumulation is always fp32) */
+#define HF_BF16 0
+#define HF_F16 1
+
+#define HF_MAX_STYLED 17 /* conv1 + convs.0..15 for size 1024 */
+#define HF_MAX_TORGB 9   /* to_rgb1 + to_rgbs.0..7 */
+
+int hf_version(void);
+const char* hf_last_error(void);
+/* Select the CUDA device for subsequent calls of this thread (the reference uses the current
+ * device of the calling thread, op/fused_bias_act_kernel.cu:54-56). */
+int hf_set_device(int device);
+int hf_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Operator boundary (models/stylegan2/op)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces upfirdn2d_op.upfirdn2d(input[major,H,W,1], kernel[kh,kw], up_x, up_y, down_x, down_y,
+ * pad_x0, pad_x1, pad_y0, pad_y1) (op/upfirdn2d.cpp:12-22, op/upfirdn2d_kernel.cu:209-369).
+ * x: [planes, in_h, in_w] fp32, y: [planes, out_h, out_w] fp32 with
+ * out = (in*up + pad0 + pad1 - k) / down + 1.  planes = N*C (minor dim is 1 on every reference
+ * call path, op/upfirdn2d.py:99). */
+int hf_upfirdn2d_f32(const float* x, float* y, const float* kernel, int planes, int in_h, int in_w,
+                     int kernel_h, int kernel_w, int up_x, int up_y, int down_x, int down_y,
+                     int pad_x0, int pad_x1, int pad_y0, int pad_y1, void* stream);
+
+/* Replaces fused.fused_bias_act(input, bias, refer, act, grad=0, alpha, scale)
+ * (op/fused_bias_act.cpp:11-21, op/fused_bias_act_kernel.cu:19-99), forward only:
+ * y[i] = act(x[i] + bias[(i / step_b) % size_b]) * scale; act: 1 = linear, 3 = leaky relu(alpha).
+ * bias may be NULL (size_b = 0). */
+int hf_bias_act_f32(const float* x, const float* bias, float* y, int64_t n, int size_b, int64_t step_b,
+                    int act, float alpha, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Module level: one StyledConv / ModulatedConv2d (models/stylegan2/model.py:183-343)
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct {
+  int cin, cout;
+  int ksize;    /* 3 (StyledConv) or 1 */
+  int upsample; /* 0 plain, 1 = conv_transpose(stride 2) + blur (model.py:252-263) */
+  int dtype;    /* HF_BF16 / HF_F16 */
+} hf_conv_desc;
+
+/* Bytes of the packed-weight blob for one conv: 16-bit GEMM operand [N,K] (+ the four polyphase
+ * kernels for upsample) followed by the fp32 demod table Wsq[cout,cin]. */
+size_t hf_conv_packed_bytes(const hf_conv_desc* d);
+
+/* Pack ModulatedConv2d.weight[1,cout,cin,k,k] (fp32; scaled by 1/sqrt(cin*k*k) here, model.py:220)
+ * and, for upsample, compose it with blur_kernel[4,4] (model.py:204-210) into the polyphase form.
+ * Once per weight load. */
+int hf_conv_pack(const hf_conv_desc* d, const float* weight, const float* blur_kernel, void* packed,
+                 void* stream);
+
+typedef struct {
+  int batch, height, width;  /* input spatial size */
+  const float* x;            /* [B,cin,H,W] fp32 NCHW; batch_stride_x = 0 broadcasts one sample */
+  int x_batch_broadcast;
+  const float* style;        /* [B, style_dim] latent rows for this layer (row stride style_stride) */
+  int style_dim;
+  int64_t style_stride;
+  const float* mod_weight;   /* conv.modulation.weight [cin, style_dim] */
+  const float* mod_bias;     /* conv.modulation.bias [cin] */
+  int demodulate;
+  /* StyledConv tail (NoiseInjection model.py:288-293 + FusedLeakyReLU op/fused_act.py:73-82);
+   * noise == NULL and act == 0 gives the bare ModulatedConv2d.forward */
+  const float* noise;        /* [noise_batch,1,Ho,Wo] or NULL */
+  int noise_batch;           /* 1 or B */
+  const float* noise_weight; /* device scalar, or NULL */
+  const float* act_bias;     /* [cout] or NULL */
+  int act;                   /* 0 none, 1 = leaky_relu(0.2) * sqrt(2) */
+  float* y;                  /* [B,cout,Ho,Wo] fp32 NCHW */
+  void* workspace;           /* hf_conv_workspace_bytes() */
+} hf_conv_io;
+
+size_t hf_conv_workspace_bytes(const hf_conv_desc* d, int batch, int height, int width);
+
+/* Replaces ModulatedConv2d.forward (model.py:238-279) / StyledConv.forward (model.py:337-343). */
+int hf_conv_forward(const hf_conv_desc* d, const void* packed, const hf_conv_io* io, void* stream);
+
+/* Replaces ToRGB.forward (model.py:356-365): modulated 1x1 conv without demodulation + bias +
+ * Upsample(skip) (model.py:35-53).  x [B,cin,H,W], skip [B,3,H/2,W/2] or NULL, y [B,3,H,W]; fp32. */
+int hf_torgb_forward(const float* x, const float* style, int64_t style_stride, int style_dim,
+                     const float* conv_weight /* [1,3,cin,1,1] */, const float* mod_weight,
+                     const float* mod_bias, const float* bias /* [1,3,1,1] */,
+                     const float* up_kernel /* [4,4] or NULL */, const float* skip, float* y, int batch,
+                     int cin, int height, int width, void* workspace /* batch*cin*4 bytes */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Generator level (models/stylegan2/model.py:368-565)
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct {
+  int size;               /* 256 / 512 / 1024 */
+  int style_dim;          /* 512 */
+  int channel_multiplier; /* 2 */
+  int dtype;              /* HF_BF16 / HF_F16 */
+} hf_gen_config;
+
+/* Device pointers to the fp32 parameters, in Generator.state_dict() naming.  Styled convs:
+ * index 0 = conv1, index i+1 = convs.{i}; ToRGB: index 0 = to_rgb1, index i+1 = to_rgbs.{i}. */
+typedef struct {
+  const float* const_input;                  /* input.input [1,C,4,4] */
+  const float* conv_weight[HF_MAX_STYLED];       /* *.conv.weight [1,cout,cin,3,3] */
+  const float* conv_mod_weight[HF_MAX_STYLED];   /* *.conv.modulation.weight [cin,style_dim] */
+  const float* conv_mod_bias[HF_MAX_STYLED];     /* *.conv.modulation.bias [cin] */
+  const float* conv_blur_kernel[HF_MAX_STYLED];  /* *.conv.blur.kernel [4,4] (upsampling convs) */
+  const float* conv_noise_weight[HF_MAX_STYLED]; /* *.noise.weight [1] */
+  const float* conv_act_bias[HF_MAX_STYLED];     /* *.activate.bias [cout] */
+  const float* rgb_weight[HF_MAX_TORGB];         /* *.conv.weight [1,3,cin,1,1] */
+  const float* rgb_mod_weight[HF_MAX_TORGB];
+  const float* rgb_mod_bias[HF_MAX_TORGB];
+  const float* rgb_bias[HF_MAX_TORGB];           /* *.bias [1,3,1,1] */
+  const float* rgb_up_kernel[HF_MAX_TORGB];      /* *.upsample.kernel [4,4] (NULL for to_rgb1) */
+} hf_gen_weights;
+
+size_t hf_generator_packed_bytes(const hf_gen_config* cfg);
+size_t hf_generator_workspace_bytes(const hf_gen_config* cfg, int batch);
+
+/* One-time repack of the generator parameters (what Net.load_weights feeds, models/Net.py:37-42). */
+int hf_generator_pack(const hf_gen_config* cfg, const hf_gen_weights* w, void* packed, void* stream);
+
+typedef struct {
+  int batch;
+  const float* latent;   /* [B, n_latent, style_dim] fp32 (input_is_latent=True, model.py:521-522) */
+  const float* noise[HF_MAX_STYLED]; /* per styled conv: [noise_batch,1,R,R] fp32 (explicit; the host
+                                        draws random noise in reference order, model.py:288-291) */
+  int noise_batch[HF_MAX_STYLED];    /* 1 = shared across the batch (registered buffers), or B */
+  int start_layer, end_layer;        /* model.py:488-489 */
+  const float* layer_in; /* [B,C,R,R] fp32 NCHW input of layer start_layer (>0), model.py:546 */
+  const float* skip_in;  /* [B,3,R,R] running RGB handed in (forward's `skip`), or NULL */
+  float* out_feature;    /* early exit: `out` [B,C,R,R] fp32 NCHW (model.py:537-538,550-551) */
+  float* out_rgb;        /* image [B,3,size,size], or the early-exit `skip` [B,3,R,R] */
+  /* FeatureStyleEncoder generator variant (pixel2style2pixel/models/stylegan2/model.py:527-560):
+   * x = (1-alpha)*x + alpha*feature_in before the conv that consumes latent index feature_idx */
+  const float* feature_in;
+  int feature_idx;
+  float feature_alpha;
+} hf_gen_io;
+
+/* Replaces Generator.forward(styles=[latent], input_is_latent=True, noise=..., layer_in, skip,
+ * start_layer, end_layer) (model.py:477-565).  Writes out_rgb (and out_feature on the early exit;
+ * *early_exit tells which return form applies: 0 = (image, None), 1 = (out, skip)). */
+int hf_generator_forward(const hf_gen_config* cfg, const void* packed, const hf_gen_io* io,
+                         void* workspace, int* early_exit /* host */, void* stream);
+
+/* Number of kernels the last hf_generator_forward / hf_conv_forward of this thread launched. */
+int hf_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAIRFAST_B200_H_ */

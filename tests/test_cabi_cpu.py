@@ -1,0 +1,114 @@
+"""CPU-side checks (no GPU): the C-ABI library builds for sm_100a, loads, exports every symbol that
+include/hairfast_b200.h declares, validates arguments without touching a device, and the host-side
+mirrors of the reference interface keep the reference's names / signatures / state_dict layout."""
+import ctypes as C
+import inspect
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from hairfastgan_b200 import build
+    build.build()
+    from hairfastgan_b200 import _lib
+    return _lib
+
+
+def test_header_symbols_all_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "hairfast_b200.h")).read()
+    declared = set(re.findall(r"\b(hf_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(lib.SYMBOLS), declared ^ set(lib.SYMBOLS)
+    handle = lib.lib()
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert handle.hf_version() == 100
+
+
+def test_library_contains_blackwell_sass(lib):
+    out = subprocess.run(["cuobjdump", "-sass", lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):      # tcgen05.mma, TMA load, tcgen05.ld
+        assert mnemonic in out, mnemonic
+
+
+def test_argument_validation_without_device(lib):
+    h = lib.lib()
+    d = lib.hf_conv_desc(64, 48, 3, 0, lib.HF_BF16)       # Cout % 32 != 0
+    assert h.hf_conv_packed_bytes(C.byref(d)) == 0
+    assert b"multiples of 32" in h.hf_last_error()
+    d = lib.hf_conv_desc(64, 64, 3, 0, lib.HF_BF16)
+    assert h.hf_conv_packed_bytes(C.byref(d)) == 64 * 9 * 64 * 2 + 64 * 64 * 4
+    d = lib.hf_conv_desc(64, 32, 3, 1, lib.HF_F16)
+    assert h.hf_conv_packed_bytes(C.byref(d)) == 4 * 32 * 9 * 64 * 2 + 32 * 64 * 4
+    cfg = lib.hf_gen_config(1024, 512, 2, lib.HF_BF16)
+    nbytes = h.hf_generator_packed_bytes(C.byref(cfg))
+    assert 100e6 < nbytes < 260e6          # 16-bit GEMM operands (4x for the polyphase up-convs) + fp32 tables
+    ws1, ws4 = h.hf_generator_workspace_bytes(C.byref(cfg), 1), h.hf_generator_workspace_bytes(C.byref(cfg), 4)
+    assert 100e6 < ws1 < 400e6 and 3.5 * ws1 < ws4 < 4.5 * ws1
+    bad = lib.hf_gen_config(1000, 512, 2, lib.HF_BF16)
+    assert h.hf_generator_packed_bytes(C.byref(bad)) == 0 and b"size 1000" in h.hf_last_error()
+    assert h.hf_upfirdn2d_f32(None, None, None, 1, 4, 4, 4, 4, 1, 1, 1, 1, 0, 0, 0, 0, None) != 0
+
+
+def test_module_surface_matches_reference_signatures():
+    """Same ctor / forward parameter names and defaults as models/stylegan2/model.py."""
+    import hairfastgan_b200.model as M
+    import hairfastgan_b200.op as op
+    assert list(inspect.signature(op.upfirdn2d).parameters) == ["input", "kernel", "up", "down", "pad"]
+    assert list(inspect.signature(op.fused_leaky_relu).parameters) == ["input", "bias", "negative_slope", "scale"]
+    assert list(inspect.signature(op.FusedLeakyReLU.__init__).parameters) == ["self", "channel", "negative_slope", "scale"]
+    fwd = inspect.signature(M.Generator.forward)
+    assert list(fwd.parameters) == ["self", "styles", "return_latents", "inject_index", "truncation",
+                                    "truncation_latent", "input_is_latent", "noise", "randomize_noise", "layer_in",
+                                    "skip", "start_layer", "end_layer", "return_rgb"]
+    assert fwd.parameters["end_layer"].default == 8 and fwd.parameters["randomize_noise"].default is True
+    assert list(inspect.signature(M.ModulatedConv2d.__init__).parameters) == [
+        "self", "in_channel", "out_channel", "kernel_size", "style_dim", "demodulate", "upsample", "downsample",
+        "blur_kernel"]
+    assert list(inspect.signature(M.StyledConv.forward).parameters) == ["self", "input", "style", "noise"]
+    assert list(inspect.signature(M.ToRGB.forward).parameters) == ["self", "input", "style", "skip"]
+
+
+def test_state_dict_layout_matches_reference_keys():
+    import hairfastgan_b200.model as M
+    from oracle import stylegan2_oracle as O
+    for size, nkeys in [(256, 135), (1024, 171)]:
+        g = M.Generator(size, 512, 8)
+        p = O.synth_generator_params(size=size, seed=0)    # keys/shapes pinned against the reference (gen_golden.py)
+        assert len(p) == nkeys
+        g.load_state_dict(p, strict=True)
+        assert g.n_latent == 2 * g.log_size - 2 and g.num_layers == 2 * (g.log_size - 2) + 1
+    up, blur = M.Upsample([1, 3, 3, 1]), g.convs[0].conv.blur
+    assert up.pad == (2, 1) and blur.pad == (1, 1)
+    assert torch.allclose(up.kernel, O.make_kernel([1, 3, 3, 1]) * 4)
+
+
+def test_cpu_inputs_fail_loudly():
+    """No CPU fallback: a CPU tensor must raise, not silently compute somewhere else."""
+    import hairfastgan_b200.model as M
+    g = M.Generator(256, 512, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        g([torch.randn(1, 14, 512)], input_is_latent=True)
+    m = M.StyledConv(64, 64, 3, 512)
+    with pytest.raises(RuntimeError):
+        m(torch.randn(1, 64, 8, 8), torch.randn(1, 512))
+
+
+def test_install_overlay_redirects_reference_imports():
+    import sys
+    import hairfastgan_b200.install as inst
+    inst.install()
+    try:
+        import importlib
+        assert importlib.import_module("models.stylegan2.op").__name__ == "hairfastgan_b200.op"
+        assert importlib.import_module("models.stylegan2.model").Generator.__module__ == "hairfastgan_b200.model"
+    finally:
+        inst.uninstall()
+    assert "models.stylegan2.op" not in sys.modules
