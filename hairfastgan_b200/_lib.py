@@ -74,6 +74,8 @@ SYMBOLS = {
     "hf_conv_pack": (C.c_int, [C.POINTER(hf_conv_desc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hf_conv_workspace_bytes": (C.c_size_t, [C.POINTER(hf_conv_desc), C.c_int, C.c_int, C.c_int]),
     "hf_conv_forward": (C.c_int, [C.POINTER(hf_conv_desc), C.c_void_p, C.POINTER(hf_conv_io), C.c_void_p]),
+    "hf_conv_time_kernel": (C.c_int, [C.POINTER(hf_conv_desc), C.c_void_p, C.POINTER(hf_conv_io), C.c_int,
+                                      C.POINTER(C.c_float), C.c_void_p]),
     "hf_torgb_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p, C.c_void_p]),

@@ -178,7 +178,21 @@ size_t hf_conv_workspace_bytes(const hf_conv_desc* d, int batch, int height, int
          align256((size_t)batch * height * width * d->cin * 2);
 }
 
+static int conv_forward_impl(const hf_conv_desc* d, const void* packed, const hf_conv_io* io, void* stream,
+                             int time_iters, float* avg_ms);
+
 int hf_conv_forward(const hf_conv_desc* d, const void* packed, const hf_conv_io* io, void* stream) {
+  return conv_forward_impl(d, packed, io, stream, 0, nullptr);
+}
+
+int hf_conv_time_kernel(const hf_conv_desc* d, const void* packed, const hf_conv_io* io, int iters, float* avg_ms,
+                        void* stream) {
+  HF_REQUIRE(iters > 0 && avg_ms, "hf_conv_time_kernel: iters must be > 0 and avg_ms non-null");
+  return conv_forward_impl(d, packed, io, stream, iters, avg_ms);
+}
+
+static int conv_forward_impl(const hf_conv_desc* d, const void* packed, const hf_conv_io* io, void* stream,
+                             int time_iters, float* avg_ms) {
   int rc = check_desc(d);
   if (rc) return rc;
   if ((rc = ensure_device())) return rc;
@@ -217,7 +231,23 @@ int hf_conv_forward(const hf_conv_desc* d, const void* packed, const hf_conv_io*
   cl.noise = io->noise; cl.noise_batch = io->noise_batch; cl.noise_w = io->noise_weight;
   cl.bias = io->act_bias; cl.act = io->act;
   cl.out_nchw = io->y;
-  return launch_conv(cl, st, nullptr);
+  if (time_iters <= 0) return launch_conv(cl, st, nullptr);
+  // warm-up launch, then `time_iters` back-to-back launches bracketed by events on the launching stream
+  if ((rc = launch_conv(cl, st, nullptr))) return rc;
+  cudaEvent_t e0, e1;
+  HF_CUDA_OK(cudaEventCreate(&e0));
+  HF_CUDA_OK(cudaEventCreate(&e1));
+  HF_CUDA_OK(cudaEventRecord(e0, st));
+  for (int i = 0; i < time_iters; ++i)
+    if ((rc = launch_conv(cl, st, nullptr))) return rc;
+  HF_CUDA_OK(cudaEventRecord(e1, st));
+  HF_CUDA_OK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  HF_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *avg_ms = ms / time_iters;
+  return HF_OK;
 }
 
 int hf_torgb_forward(const float* x, const float* style, int64_t style_stride, int style_dim,

@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_general_kernel(const float* __r
 int launch_upfirdn2d(const float* x, float* y, const float* k, int planes, int in_h, int in_w, int kh, int kw,
                      int up_x, int up_y, int down_x, int down_y, int px0, int px1, int py0, int py1,
                      cudaStream_t st) {
+  if (planes == 0) return HF_OK;
   HF_REQUIRE(x && y && k, "upfirdn2d: null pointer");
   HF_REQUIRE(planes >= 0 && in_h > 0 && in_w > 0 && kh > 0 && kw > 0, "upfirdn2d: bad shape");
   HF_REQUIRE(up_x > 0 && up_y > 0 && down_x > 0 && down_y > 0, "upfirdn2d: up/down must be positive");
@@ -220,6 +221,7 @@ __global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__
 
 int launch_bias_act(const float* x, const float* b, float* y, int64_t n, int size_b, int64_t step_b, int act,
                     float alpha, float scale, cudaStream_t st) {
+  if (n == 0) return HF_OK;
   HF_REQUIRE(x && y, "bias_act: null pointer");
   HF_REQUIRE(act == 1 || act == 3, "bias_act: act must be 1 (linear) or 3 (leaky relu), got %d", act);
   HF_REQUIRE(n >= 0 && size_b >= 0 && step_b >= 1, "bias_act: bad sizes");

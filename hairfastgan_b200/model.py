@@ -414,12 +414,12 @@ class Generator(nn.Module):
         return cfg
 
     def _get_workspace(self, cfg, batch, device):
-        key = (batch, str(device), cfg.dtype)
-        ws = self._workspace.get(key)
-        if ws is None:
-            nbytes = _lib.lib().hf_generator_workspace_bytes(C.byref(cfg), batch)
-            self._workspace = {key: _alloc_bytes(nbytes, device)}     # keep one (largest recent) workspace
-            ws = self._workspace[key]
+        # one grow-only buffer per device: the layout is recomputed from (cfg, batch) on every call, so a
+        # workspace sized for a larger batch serves every smaller one
+        nbytes = _lib.lib().hf_generator_workspace_bytes(C.byref(cfg), batch)
+        ws = self._workspace.get(str(device))
+        if ws is None or ws.numel() < nbytes:
+            ws = self._workspace[str(device)] = _alloc_bytes(nbytes, device)
         return ws
 
     # ------------------------------------------------------------------ forward

@@ -107,6 +107,12 @@ size_t hf_conv_workspace_bytes(const hf_conv_desc* d, int batch, int height, int
 /* Replaces ModulatedConv2d.forward (model.py:238-279) / StyledConv.forward (model.py:337-343). */
 int hf_conv_forward(const hf_conv_desc* d, const void* packed, const hf_conv_io* io, void* stream);
 
+/* Measurement helper (no reference counterpart): runs hf_conv_forward's prologue once, then the
+ * tcgen05 convolution kernel alone `iters` times between two CUDA events recorded on `stream`, and
+ * returns the average kernel duration in milliseconds (host pointer).  Synchronises the stream. */
+int hf_conv_time_kernel(const hf_conv_desc* d, const void* packed, const hf_conv_io* io, int iters,
+                        float* avg_ms /* host */, void* stream);
+
 /* Replaces ToRGB.forward (model.py:356-365): modulated 1x1 conv without demodulation + bias +
  * Upsample(skip) (model.py:35-53).  x [B,cin,H,W], skip [B,3,H/2,W/2] or NULL, y [B,3,H,W]; fp32. */
 int hf_torgb_forward(const float* x, const float* style, int64_t style_stride, int style_dim,

@@ -55,6 +55,7 @@ def test_argument_validation_without_device(lib):
     bad = lib.hf_gen_config(1000, 512, 2, lib.HF_BF16)
     assert h.hf_generator_packed_bytes(C.byref(bad)) == 0 and b"size 1000" in h.hf_last_error()
     assert h.hf_upfirdn2d_f32(None, None, None, 1, 4, 4, 4, 4, 1, 1, 1, 1, 0, 0, 0, 0, None) != 0
+    assert h.hf_upfirdn2d_f32(None, None, None, 0, 4, 4, 4, 4, 1, 1, 1, 1, 0, 0, 0, 0, None) == 0   # empty input
 
 
 def test_module_surface_matches_reference_signatures():
