@@ -161,6 +161,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int w_l = row % p.TW, h_l = (row / p.TW) % p.TH, bb = row / (p.TW * p.TH);
     const float nw = p.noise_w ? __ldg(p.noise_w) : 0.f;
     const int chunks = p.n_tile / 32;
+    const int nc_tile = p.up ? p.n_tile / 4 : p.n_tile;   // output channels per tile
     const size_t plane_o = (size_t)p.Ho * p.Wo;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -170,10 +171,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int n0 = nt * p.n_tile;
       const bool valid = b < p.B;
       // ---- per-tile table: demod, bias, next-layer style scale, ToRGB weights, indexed [bb][col]
-      for (int e = etid; e < p.TB * p.n_tile; e += 128) {
-        const int ebb = e / p.n_tile, col = e - ebb * p.n_tile;
+      // (one entry per output channel of the tile: the four parity column groups of an up-conv share it)
+      for (int e = etid; e < p.TB * nc_tile; e += 128) {
+        const int ebb = e / nc_tile, ol = e - ebb * nc_tile;
         const int eb = bt * p.TB + ebb;
-        const int o = p.up ? (n0 >> 2) + (col >> 7) * 32 + (col & 31) : n0 + col;
+        const int o = (p.up ? (n0 >> 2) : n0) + ol;
         TableEntry t;
         t.d = 1.f; t.bias = 0.f; t.s_next = 1.f; t.pad = 0.f; t.w0 = t.w1 = t.w2 = 0.f; t.pad2 = 0.f;
         if (eb < p.B) {
@@ -209,7 +211,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * 256);
-      const TableEntry* trow = table + bb * p.n_tile;
+      const TableEntry* trow = table + bb * nc_tile;
       float rgb[4][3];
 #pragma unroll
       for (int i = 0; i < 4; ++i) rgb[i][0] = rgb[i][1] = rgb[i][2] = 0.f;
@@ -223,7 +225,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_arrive(&tmem_empty[buf]);
         }
         const int par = p.up ? (q & 3) : 0;
-        const int o_base = p.up ? (n0 >> 2) + (q >> 2) * 32 : n0 + q * 32;
+        const int t_base = p.up ? (q >> 2) * 32 : q * 32;          // channel offset inside the tile
+        const int o_base = (p.up ? (n0 >> 2) : n0) + t_base;
         const int yo = p.up ? 2 * y + (par >> 1) : y;
         const int xo = p.up ? 2 * x + (par & 1) : x;
         const float nzv = nz[par];
@@ -237,7 +240,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           float v[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const TableEntry& t = trow[q * 32 + j + u];
+            const TableEntry& t = trow[t_base + j + u];
             float a = fmaf(__uint_as_float(acc[j + u]), t.d, nzv + t.bias);
             if (p.act) a = (a > 0.f ? a : 0.2f * a) * kSqrt2;
             r0 = fmaf(a, t.w0, r0); r1 = fmaf(a, t.w1, r1); r2 = fmaf(a, t.w2, r2);
@@ -306,12 +309,13 @@ int conv_plan(const ConvLaunch& a, ConvPlan* p) {
     n_tile = a.force_n_tile;
   } else {
     for (int cand = 256; cand >= nmin; cand >>= 1) {
-      if (ntot % cand || p->TB * cand > 512) continue;
+      if (ntot % cand || p->TB * (a.up ? cand / 4 : cand) > 512) continue;
       n_tile = cand;
       if ((int64_t)p->num_m_tiles * (ntot / cand) >= sms) break;   // largest tile that still fills the GPU
     }
   }
-  HF_REQUIRE(n_tile >= nmin && n_tile <= 256 && ntot % n_tile == 0 && n_tile % 32 == 0 && p->TB * n_tile <= 512,
+  HF_REQUIRE(n_tile >= nmin && n_tile <= 256 && ntot % n_tile == 0 && n_tile % 32 == 0 &&
+                 p->TB * (a.up ? n_tile / 4 : n_tile) <= 512,
              "conv: no valid N tile (Ntot=%d, n_tile=%d, TB=%d)", ntot, n_tile, p->TB);
   p->n_tile = n_tile;
   p->num_n_tiles = ntot / n_tile;
