@@ -73,6 +73,7 @@ SYMBOLS = {
     "hf_conv_packed_bytes": (C.c_size_t, [C.POINTER(hf_conv_desc)]),
     "hf_conv_pack": (C.c_int, [C.POINTER(hf_conv_desc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hf_conv_workspace_bytes": (C.c_size_t, [C.POINTER(hf_conv_desc), C.c_int, C.c_int, C.c_int]),
+    "hf_conv_plan_query": (C.c_int, [C.POINTER(hf_conv_desc), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "hf_conv_forward": (C.c_int, [C.POINTER(hf_conv_desc), C.c_void_p, C.POINTER(hf_conv_io), C.c_void_p]),
     "hf_conv_time_kernel": (C.c_int, [C.POINTER(hf_conv_desc), C.c_void_p, C.POINTER(hf_conv_io), C.c_int,
                                       C.POINTER(C.c_float), C.c_void_p]),

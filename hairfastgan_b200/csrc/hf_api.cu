@@ -178,6 +178,22 @@ size_t hf_conv_workspace_bytes(const hf_conv_desc* d, int batch, int height, int
          align256((size_t)batch * height * width * d->cin * 2);
 }
 
+int hf_conv_plan_query(const hf_conv_desc* d, int batch, int height, int width, int* out) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  HF_REQUIRE(out, "hf_conv_plan_query: null output");
+  ConvLaunch cl;
+  memset(&cl, 0, sizeof(cl));
+  cl.B = batch; cl.H = height; cl.W = width; cl.Cin = d->cin; cl.Cout = d->cout;
+  cl.taps = d->ksize * d->ksize; cl.up = d->upsample; cl.dtype = d->dtype;
+  ConvPlan pl;
+  if ((rc = conv_plan(cl, &pl))) return rc;
+  const int v[12] = {pl.halo, pl.n_tile, pl.num_n_tiles, pl.G, pl.na_slots, pl.pitch, pl.b_resident, pl.stages,
+                     (int)pl.smem_bytes, pl.num_tiles, pl.grid, pl.kchunk};
+  for (int i = 0; i < 12; ++i) out[i] = v[i];
+  return HF_OK;
+}
+
 static int conv_forward_impl(const hf_conv_desc* d, const void* packed, const hf_conv_io* io, void* stream,
                              int time_iters, float* avg_ms);
 

@@ -174,6 +174,36 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// Warp-collective variants: executed convergently by all 32 lanes with warp-uniform operands; one lane
+// is elected INSIDE the asm block.  Keeping the control flow uniform lets the compiler hold the
+// descriptors in uniform registers instead of wrapping every UTCHMMA in an R2UR waterfall loop (measured:
+// the `if (lane == 0)` form cost ~450 issue cycles per conv tap, see profiles/).
+__device__ __forceinline__ void umma_f16_warp(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar))
+      : "memory");
+}
+// High 32 bits of a K-major descriptor (SBO, version, layout); the low word is (addr >> 4) | LBO.
+__device__ __forceinline__ uint32_t kmajor_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | ((layout_type & 7) << 29);
+}
+__device__ __forceinline__ uint64_t kmajor_desc(uint32_t hi, uint32_t smem_addr) {
+  return ((uint64_t)hi << 32) | (uint64_t)(((smem_addr & 0x3FFFF) >> 4) | (1u << 16));
+}
+
 // 32 lanes x 32 consecutive fp32 columns; thread i of the warp gets lane (base_lane + i).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(

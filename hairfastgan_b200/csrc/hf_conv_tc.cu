@@ -7,21 +7,32 @@
 // 16-bit NHWC activation `xh` by the producer of that tensor, the demodulation d[b,o] is applied to
 // the fp32 accumulator in the epilogue).  The upsampling conv (conv_transpose2d stride 2 + 4x4 blur,
 // model.py:252-263) runs as four 3x3 correlations, one per output parity, stacked along GEMM-N
-// (Appendix C-2), so the same kernel serves both.
+// (Appendix C-2), so the same kernels serve both.
 //
-// GEMM view per CTA tile:  D[128 pixels, n_tile] += A[128 pixels, 64 ch] * B[n_tile, 64 ch]^T over
-// taps x channel chunks.  A = one TMA 4-D box (64ch, TW, TH, TB) of the NHWC activation shifted by
-// the tap offset (out-of-bounds rows/cols are zero-filled by TMA = the conv padding); B = one TMA
-// 2-D box of the packed weights.  Both land in 128B-swizzled K-major shared memory and feed
-// tcgen05.mma (kind::f16, fp32 accumulators in TMEM).  Warp roles: warp 0 = TMA producer, warp 1 =
-// MMA issuer (+ TMEM alloc), warps 2-5 = epilogue (TMEM -> registers -> demod/noise/bias/lrelu ->
-// {16-bit NHWC for the next conv, fp32 NCHW, fused ToRGB partial sums}).  Persistent CTAs, static
-// tile schedule, double-buffered accumulators so the epilogue of tile i overlaps the MMAs of i+1.
+// GEMM view per tile:  D[128 pixels, n_tile] += A[128 pixels, 64 ch] * B[n_tile, 64 ch]^T over taps x
+// channel chunks; operands in swizzled K-major shared memory, tcgen05.mma kind::f16 with fp32
+// accumulators in TMEM, persistent CTAs with a static schedule, two accumulator buffers.
+//
+// Two kernels share the epilogue:
+//  * conv_halo_kernel (H % 16 == 0, W % 8 == 0): per 64-channel chunk ONE TMA 4-D box brings the
+//    (16+2) x (8+2)-pixel halo of an 8x16-pixel tile into a ring slot; the nine taps are nine UMMA
+//    descriptors that start (dy*pitch + dx) rows into that slot with SBO = one halo row (measured on
+//    B200: the 128B swizzle is a function of absolute smem address bits, so unaligned starts and a
+//    non-1024-multiple SBO are fine with base_offset = 0).  Each activation byte crosses L2->smem once
+//    per chunk instead of nine times.  Work is scheduled in ROUNDS of G consecutive tiles that share
+//    one 256-column accumulator buffer (G * n_tile <= 256), so narrow layers amortise every barrier /
+//    commit over the same amount of work as a wide one, and each weight tile is reused by G tiles.
+//    Weights either stay RESIDENT in smem for the whole kernel (single channel chunk, single N tile) or
+//    stream through their own TMA ring.  Two 4-warp epilogue groups alternate rounds.
+//  * conv_igemm_kernel (any shape; used for 4^2 / 8^2): one TMA box per (tap, chunk) shifted by the tap
+//    offset; the 128 GEMM rows may span several batch samples (4x4x8, 8x8x2).
+// In both, TMA out-of-bounds zero fill *is* the conv zero padding.
+#include <stdlib.h>
+
 #include "hf_kernels.cuh"
 
 namespace hf {
 
-constexpr int kConvThreads = 192;
 constexpr int kMaxStages = 8;
 constexpr int kTableBytes = 16384;   // 512 entries x 32 B
 constexpr float kSqrt2 = 1.41421356237309515f;
@@ -31,12 +42,16 @@ struct ConvKernelParams {
   int Ho, Wo;
   int taps, up, act;
   int TW, TH, TB, tiles_x, tiles_y;
-  int n_tile, num_n_tiles, num_tiles;
+  int n_tile, num_n_tiles, num_tiles;   // num_tiles = work items (tiles for v1, rounds x N tiles for halo)
+  int num_m_tiles;
   int num_kb;              // taps * Cin / KCHUNK
   int kc_per_tap;          // Cin / KCHUNK
-  int stages;
+  int stages;              // v1: A+B stages; halo: B stages (stream mode)
   uint32_t stage_bytes, a_bytes;
   uint32_t idesc;
+  // halo kernel
+  int G, na_slots, pitch, b_resident;
+  uint32_t a_slot_bytes;
   const float* d;
   const float* noise;
   int64_t noise_bstride;
@@ -54,6 +69,134 @@ struct __align__(16) TableEntry {
   float d, bias, s_next, pad;
   float w0, w1, w2, pad2;
 };
+
+struct MTile {
+  int x0, y0, bt;
+};
+__device__ __forceinline__ MTile decode_mtile(const ConvKernelParams& p, int mt) {
+  MTile t;
+  t.x0 = (mt % p.tiles_x) * p.TW;
+  t.y0 = ((mt / p.tiles_x) % p.tiles_y) * p.TH;
+  t.bt = mt / (p.tiles_x * p.tiles_y);
+  return t;
+}
+
+// Per-tile table {demod, bias, next-layer style scale, ToRGB weights}, indexed [bb][channel in tile]
+// (the four parity column groups of an up-conv share an entry).  Called by the 128 threads of one group.
+__device__ __forceinline__ void fill_table(const ConvKernelParams& p, TableEntry* table, int etid, int bt, int n0) {
+  const int nc_tile = p.up ? p.n_tile / 4 : p.n_tile;
+  for (int e = etid; e < p.TB * nc_tile; e += 128) {
+    const int ebb = e / nc_tile, ol = e - ebb * nc_tile;
+    const int eb = bt * p.TB + ebb;
+    const int o = (p.up ? (n0 >> 2) : n0) + ol;
+    TableEntry t;
+    t.d = 1.f; t.bias = 0.f; t.s_next = 1.f; t.pad = 0.f; t.w0 = t.w1 = t.w2 = 0.f; t.pad2 = 0.f;
+    if (eb < p.B) {
+      const size_t bo = (size_t)eb * p.Cout + o;
+      if (p.d) t.d = __ldg(p.d + bo);
+      if (p.bias) t.bias = __ldg(p.bias + o);
+      if (p.s_next) t.s_next = __ldg(p.s_next + bo);
+      if (p.rgb_w) {
+        const float rs = __ldg(p.rgb_s + bo);
+        t.w0 = __ldg(p.rgb_w + o) * rs;
+        t.w1 = __ldg(p.rgb_w + p.Cout + o) * rs;
+        t.w2 = __ldg(p.rgb_w + 2 * p.Cout + o) * rs;
+      }
+    }
+    table[e] = t;
+  }
+}
+
+// nw * noise for one pixel (plain: .x) or its 2x2 output quad (up: x,y = top row; z,w = bottom row)
+__device__ __forceinline__ float4 load_noise(const ConvKernelParams& p, int b, int y, int x, float nw) {
+  float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.noise) {
+    const float* np_ = p.noise + (size_t)b * p.noise_bstride;
+    if (p.up) {
+      const float* r0 = np_ + (size_t)(2 * y) * p.Wo + 2 * x;
+      const float2 a = __ldg(reinterpret_cast<const float2*>(r0));
+      const float2 c = __ldg(reinterpret_cast<const float2*>(r0 + p.Wo));
+      nz = make_float4(nw * a.x, nw * a.y, nw * c.x, nw * c.y);
+    } else {
+      nz.x = nw * __ldg(np_ + (size_t)y * p.Wo + x);
+    }
+  }
+  return nz;
+}
+
+// TMEM -> registers -> fused epilogue -> global, for one tile and one thread (= one GEMM row = one pixel).
+//   a = acc*d + nw*noise + bias ; a = lrelu(a)*sqrt2 ; rgb += a*wrgb ; out16 = a*s_next
+// `release_bar` != nullptr: arrive on it right after the last TMEM read (hands the accumulator back).
+template <int DT>
+__device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, const TableEntry* trow, uint32_t taddr,
+                                              uint64_t* release_bar, int n0, int nt, int b, int y, int x, bool valid,
+                                              float4 nz) {
+  const int chunks = p.n_tile / 32;
+  const size_t plane_o = (size_t)p.Ho * p.Wo;
+  float rgb[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rgb[i][0] = rgb[i][1] = rgb[i][2] = 0.f;
+
+  for (int q = 0; q < chunks; ++q) {
+    uint32_t acc[32];
+    tmem_ld_32x32(taddr + q * 32, acc);
+    tmem_ld_wait();
+    if (release_bar && q == chunks - 1) {
+      tc_fence_before();
+      mbar_arrive(release_bar);
+    }
+    const int par = p.up ? (q & 3) : 0;
+    const int t_base = p.up ? (q >> 2) * 32 : q * 32;          // channel offset inside the tile
+    const int o_base = (p.up ? (n0 >> 2) : n0) + t_base;
+    const int yo = p.up ? 2 * y + (par >> 1) : y;
+    const int xo = p.up ? 2 * x + (par & 1) : x;
+    const float nzv = par == 0 ? nz.x : (par == 1 ? nz.y : (par == 2 ? nz.z : nz.w));
+    uint32_t packed[16];
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    float* onchw = (p.out_nchw && valid) ? p.out_nchw + ((size_t)b * p.Cout + o_base) * plane_o +
+                                              (size_t)yo * p.Wo + xo
+                                            : nullptr;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      float v[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const TableEntry& t = trow[t_base + j + u];
+        float a = fmaf(__uint_as_float(acc[j + u]), t.d, nzv + t.bias);
+        if (p.act) a = (a > 0.f ? a : 0.2f * a) * kSqrt2;
+        r0 = fmaf(a, t.w0, r0); r1 = fmaf(a, t.w1, r1); r2 = fmaf(a, t.w2, r2);
+        if (onchw) onchw[(size_t)(j + u) * plane_o] = a;
+        v[u] = a * t.s_next;
+      }
+      packed[j >> 1] = Half2T<DT>::pack(v[0], v[1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i == par) { rgb[i][0] += r0; rgb[i][1] += r1; rgb[i][2] += r2; }
+    if (p.xhat_out && valid) {
+      uint4* dst = reinterpret_cast<uint4*>(p.xhat_out + (((size_t)b * p.Ho + yo) * p.Wo + xo) * p.Cout + o_base);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+    }
+  }
+  if (p.rgb_partial && valid) {
+    float* pp = p.rgb_partial + ((size_t)nt * p.B + b) * 3 * plane_o;
+#pragma unroll
+    for (int par = 0; par < 4; ++par) {
+      if (par > 0 && !p.up) break;
+      const int yo = p.up ? 2 * y + (par >> 1) : y;
+      const int xo = p.up ? 2 * x + (par & 1) : x;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) pp[(size_t)j * plane_o + (size_t)yo * p.Wo + xo] = rgb[par][j];
+    }
+  }
+}
+
+// =============================================================================================
+// v1: one TMA box per (tap, channel chunk)
+// =============================================================================================
+constexpr int kConvThreads = 192;
 
 template <int KCHUNK, int DT>
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -106,9 +249,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int pad = (p.taps == 9) ? 1 : 0;
       const uint32_t tx_bytes = p.stage_bytes;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.num_n_tiles, mt = tile / p.num_n_tiles;
-        const int xt = mt % p.tiles_x, yt = (mt / p.tiles_x) % p.tiles_y, bt = mt / (p.tiles_x * p.tiles_y);
-        const int x0 = xt * p.TW, y0 = yt * p.TH, b0 = bt * p.TB, n0 = nt * p.n_tile;
+        const int nt = tile % p.num_n_tiles;
+        const MTile tc = decode_mtile(p, tile / p.num_n_tiles);
+        const int b0 = tc.bt * p.TB, n0 = nt * p.n_tile;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dy = (p.taps == 9) ? tap / 3 : 0, dx = (p.taps == 9) ? tap % 3 : 0;
           for (int kc = 0; kc < p.kc_per_tap; ++kc) {
@@ -116,7 +259,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint8_t* a_dst = stage_base + (size_t)stage * p.stage_bytes;
             uint8_t* b_dst = a_dst + p.a_bytes;
             mbar_expect_tx(&full_bar[stage], tx_bytes);
-            tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * KCHUNK, x0 + dx - pad, y0 + dy - pad, b0);
+            tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * KCHUNK, tc.x0 + dx - pad, tc.y0 + dy - pad, b0);
             tma_load_2d(b_dst, &tmB, &full_bar[stage], tap * p.Cin + kc * KCHUNK, n0);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
@@ -125,9 +268,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
+    // (whole warp, uniform control flow; one lane is elected inside umma_*_warp)
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    const uint32_t smem_base_u32 = smem_u32(stage_base);
+    const uint32_t desc_hi = kmajor_desc_hi(SBO, LAYOUT);
+    const uint32_t idesc = p.idesc;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
@@ -137,19 +284,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(stage_base + (size_t)stage * p.stage_bytes);
+        {
+          const uint32_t a_addr = smem_base_u32 + (uint32_t)stage * p.stage_bytes;
           const uint32_t b_addr = a_addr + p.a_bytes;
 #pragma unroll
-          for (int k = 0; k < KCHUNK / 16; ++k) {
-            const uint64_t adesc = make_kmajor_desc(a_addr + k * 32, SBO, LAYOUT);
-            const uint64_t bdesc = make_kmajor_desc(b_addr + k * 32, SBO, LAYOUT);
-            umma_f16(tmem_d, adesc, bdesc, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);                    // frees the smem slot when the MMAs retire
-          if (kb == p.num_kb - 1) umma_commit(&tmem_full[buf]);   // accumulator ready for the epilogue
+          for (int k = 0; k < KCHUNK / 16; ++k)
+            umma_f16_warp(tmem_d, kmajor_desc(desc_hi, a_addr + k * 32), kmajor_desc(desc_hi, b_addr + k * 32), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_warp(&empty_bar[stage]);                    // frees the smem slot when the MMAs retire
+          if (kb == p.num_kb - 1) umma_commit_warp(&tmem_full[buf]);   // accumulator ready for the epilogue
         }
-        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -160,114 +304,256 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int etid = (warp - 2) * 32 + lane; // 0..127
     const int w_l = row % p.TW, h_l = (row / p.TW) % p.TH, bb = row / (p.TW * p.TH);
     const float nw = p.noise_w ? __ldg(p.noise_w) : 0.f;
-    const int chunks = p.n_tile / 32;
-    const int nc_tile = p.up ? p.n_tile / 4 : p.n_tile;   // output channels per tile
-    const size_t plane_o = (size_t)p.Ho * p.Wo;
+    const int nc_tile = p.up ? p.n_tile / 4 : p.n_tile;
     int it = 0;
+    int cached_bt = -1, cached_nt = -1;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int nt = tile % p.num_n_tiles, mt = tile / p.num_n_tiles;
-      const int xt = mt % p.tiles_x, yt = (mt / p.tiles_x) % p.tiles_y, bt = mt / (p.tiles_x * p.tiles_y);
-      const int x = xt * p.TW + w_l, y = yt * p.TH + h_l, b = bt * p.TB + bb;
+      const int nt = tile % p.num_n_tiles;
+      const MTile tc = decode_mtile(p, tile / p.num_n_tiles);
+      const int x = tc.x0 + w_l, y = tc.y0 + h_l, b = tc.bt * p.TB + bb;
       const int n0 = nt * p.n_tile;
       const bool valid = b < p.B;
-      // ---- per-tile table: demod, bias, next-layer style scale, ToRGB weights, indexed [bb][col]
-      // (one entry per output channel of the tile: the four parity column groups of an up-conv share it)
-      for (int e = etid; e < p.TB * nc_tile; e += 128) {
-        const int ebb = e / nc_tile, ol = e - ebb * nc_tile;
-        const int eb = bt * p.TB + ebb;
-        const int o = (p.up ? (n0 >> 2) : n0) + ol;
-        TableEntry t;
-        t.d = 1.f; t.bias = 0.f; t.s_next = 1.f; t.pad = 0.f; t.w0 = t.w1 = t.w2 = 0.f; t.pad2 = 0.f;
-        if (eb < p.B) {
-          const size_t bo = (size_t)eb * p.Cout + o;
-          if (p.d) t.d = __ldg(p.d + bo);
-          if (p.bias) t.bias = __ldg(p.bias + o);
-          if (p.s_next) t.s_next = __ldg(p.s_next + bo);
-          if (p.rgb_w) {
-            const float rs = __ldg(p.rgb_s + bo);
-            t.w0 = __ldg(p.rgb_w + o) * rs;
-            t.w1 = __ldg(p.rgb_w + p.Cout + o) * rs;
-            t.w2 = __ldg(p.rgb_w + 2 * p.Cout + o) * rs;
-          }
-        }
-        table[e] = t;
+      if (tc.bt != cached_bt || nt != cached_nt) {     // table depends on (batch tile, N tile) only
+        named_bar_sync(1, 128);
+        fill_table(p, table, etid, tc.bt, n0);
+        named_bar_sync(1, 128);
+        cached_bt = tc.bt; cached_nt = nt;
       }
-      // ---- noise for this pixel (plain) / its 2x2 output quad (up)
-      float nz[4] = {0.f, 0.f, 0.f, 0.f};
-      if (p.noise && valid) {
-        const float* np_ = p.noise + (size_t)b * p.noise_bstride;
-        if (p.up) {
-#pragma unroll
-          for (int par = 0; par < 4; ++par)
-            nz[par] = nw * __ldg(np_ + (size_t)(2 * y + (par >> 1)) * p.Wo + 2 * x + (par & 1));
-        } else {
-          nz[0] = nw * __ldg(np_ + (size_t)y * p.Wo + x);
-        }
-      }
-      named_bar_sync(1, 128);
-
+      const float4 nz = valid ? load_noise(p, b, y, x, nw) : make_float4(0.f, 0.f, 0.f, 0.f);
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * 256);
-      const TableEntry* trow = table + bb * nc_tile;
-      float rgb[4][3];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) rgb[i][0] = rgb[i][1] = rgb[i][2] = 0.f;
+      epilogue_tile<DT>(p, table + bb * nc_tile, taddr, &tmem_empty[buf], n0, nt, b, y, x, valid, nz);
+    }
+  }
 
-      for (int q = 0; q < chunks; ++q) {
-        uint32_t acc[32];
-        tmem_ld_32x32(taddr + q * 32, acc);
-        tmem_ld_wait();
-        if (q == chunks - 1) {     // accumulator fully read: hand the TMEM buffer back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(&tmem_empty[buf]);
-        }
-        const int par = p.up ? (q & 3) : 0;
-        const int t_base = p.up ? (q >> 2) * 32 : q * 32;          // channel offset inside the tile
-        const int o_base = (p.up ? (n0 >> 2) : n0) + t_base;
-        const int yo = p.up ? 2 * y + (par >> 1) : y;
-        const int xo = p.up ? 2 * x + (par & 1) : x;
-        const float nzv = nz[par];
-        uint32_t packed[16];
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-        float* onchw = (p.out_nchw && valid) ? p.out_nchw + ((size_t)b * p.Cout + o_base) * plane_o +
-                                                  (size_t)yo * p.Wo + xo
-                                                : nullptr;
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float v[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const TableEntry& t = trow[t_base + j + u];
-            float a = fmaf(__uint_as_float(acc[j + u]), t.d, nzv + t.bias);
-            if (p.act) a = (a > 0.f ? a : 0.2f * a) * kSqrt2;
-            r0 = fmaf(a, t.w0, r0); r1 = fmaf(a, t.w1, r1); r2 = fmaf(a, t.w2, r2);
-            if (onchw) onchw[(size_t)(j + u) * plane_o] = a;
-            v[u] = a * t.s_next;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =============================================================================================
+// halo kernel: halo tile ring in smem, nine taps = nine shifted UMMA descriptors, rounds of G tiles
+// =============================================================================================
+constexpr int kHaloThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 two epilogue groups
+constexpr int kHaloTW = 8, kHaloTH = 16;
+constexpr int kHaloRows = kHaloTH + 2;
+constexpr int kMaxASlots = 8;
+constexpr int kMaxG = 8;
+
+template <int KCHUNK, int DT>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const ConvKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr uint32_t ROW_BYTES = KCHUNK * 2;
+  constexpr uint32_t SBO_B = 8 * ROW_BYTES;
+  constexpr uint32_t LAYOUT = (KCHUNK == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
+  const uint32_t a_slot = p.a_slot_bytes;
+  const uint32_t a_tx = (uint32_t)kHaloRows * p.pitch * ROW_BYTES;     // bytes one halo box delivers
+  const uint32_t tap_bytes = (uint32_t)p.n_tile * ROW_BYTES;           // one tap of weights
+  const int b_slots = p.b_resident ? 9 : p.stages;
+  uint8_t* a_base = smem;                                              // [na_slots][a_slot]
+  uint8_t* b_base = smem + (size_t)p.na_slots * a_slot;                // [b_slots][tap_bytes]
+  TableEntry* table = reinterpret_cast<TableEntry*>(b_base + (size_t)b_slots * tap_bytes);   // 2 x 8 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(table) + kTableBytes);
+  uint64_t* b_full = bars;                          // [kMaxStages]
+  uint64_t* b_empty = b_full + kMaxStages;          // [kMaxStages]
+  uint64_t* a_full = b_empty + kMaxStages;          // [kMaxASlots]
+  uint64_t* a_empty = a_full + kMaxASlots;          // [kMaxASlots]
+  uint64_t* tmem_full = a_empty + kMaxASlots;       // [2]
+  uint64_t* tmem_empty = tmem_full + 2;             // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int G = p.G, NA = p.na_slots;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int i = 0; i < kMaxASlots; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int bs = 0, as = 0;
+      uint32_t bphase = 0, aphase = 0;
+      if (p.b_resident) {                    // whole weight matrix of this layer: loaded once, never released
+        mbar_expect_tx(&b_full[0], 9 * tap_bytes);
+        for (int tap = 0; tap < 9; ++tap)
+          tma_load_2d(b_base + (size_t)tap * tap_bytes, &tmB, &b_full[0], tap * p.Cin, 0);
+      }
+      for (int w = blockIdx.x; w < p.num_tiles; w += gridDim.x) {
+        const int nt = w % p.num_n_tiles, m0 = (w / p.num_n_tiles) * G;
+        const int gcount = min(G, p.num_m_tiles - m0);
+        const int n0 = nt * p.n_tile;
+        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+          for (int g = 0; g < gcount; ++g) {
+            const MTile tc = decode_mtile(p, m0 + g);
+            mbar_wait(&a_empty[as], aphase ^ 1);
+            mbar_expect_tx(&a_full[as], a_tx);
+            tma_load_4d(a_base + (size_t)as * a_slot, &tmA, &a_full[as], kc * KCHUNK, tc.x0 - 1, tc.y0 - 1, tc.bt);
+            if (++as == NA) { as = 0; aphase ^= 1; }
           }
-          packed[j >> 1] = Half2T<DT>::pack(v[0], v[1]);
-        }
-        rgb[par][0] += r0; rgb[par][1] += r1; rgb[par][2] += r2;
-        if (p.xhat_out && valid) {
-          uint4* dst = reinterpret_cast<uint4*>(p.xhat_out + (((size_t)b * p.Ho + yo) * p.Wo + xo) * p.Cout + o_base);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-        }
-      }
-      if (p.rgb_partial && valid) {
-        float* pp = p.rgb_partial + ((size_t)nt * p.B + b) * 3 * plane_o;
-        const int npar = p.up ? 4 : 1;
-        for (int par = 0; par < npar; ++par) {
-          const int yo = p.up ? 2 * y + (par >> 1) : y;
-          const int xo = p.up ? 2 * x + (par & 1) : x;
-#pragma unroll
-          for (int j = 0; j < 3; ++j) pp[(size_t)j * plane_o + (size_t)yo * p.Wo + xo] = rgb[par][j];
+          if (!p.b_resident) {
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&b_empty[bs], bphase ^ 1);
+              mbar_expect_tx(&b_full[bs], tap_bytes);
+              tma_load_2d(b_base + (size_t)bs * tap_bytes, &tmB, &b_full[bs], tap * p.Cin + kc * KCHUNK, n0);
+              if (++bs == p.stages) { bs = 0; bphase ^= 1; }
+            }
+          }
         }
       }
-      named_bar_sync(1, 128);    // table is rewritten by the next tile
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    // (whole warp, uniform control flow; one lane is elected inside umma_*_warp)
+    int bs = 0, as = 0;
+    uint32_t bphase = 0, aphase = 0;
+    int it = 0;
+    const uint32_t a_base_u32 = smem_u32(a_base), b_base_u32 = smem_u32(b_base);
+    const uint32_t sbo_a = (uint32_t)p.pitch * ROW_BYTES;            // next 8-pixel group = next halo row
+    const uint32_t hi_a = kmajor_desc_hi(sbo_a, LAYOUT), hi_b = kmajor_desc_hi(SBO_B, LAYOUT);
+    const uint32_t idesc = p.idesc;
+    const uint32_t n_tile = (uint32_t)p.n_tile;
+    if (p.b_resident) {
+      mbar_wait(&b_full[0], 0);
+      tc_fence_after();
+    }
+    for (int w = blockIdx.x; w < p.num_tiles; w += gridDim.x, ++it) {
+      const int m0 = (w / p.num_n_tiles) * G;
+      const int gcount = min(G, p.num_m_tiles - m0);
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 256);
+      if (p.b_resident) {
+        // order (tile g, tap): each halo slot is released as soon as its nine taps are issued
+        for (int g = 0; g < gcount; ++g) {
+          mbar_wait(&a_full[as], aphase);
+          tc_fence_after();
+          const uint32_t a_addr = a_base_u32 + (uint32_t)as * a_slot;
+          const uint32_t d_addr = tmem_d + (uint32_t)g * n_tile;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t a_tap = a_addr + (uint32_t)((tap / 3) * p.pitch + (tap % 3)) * ROW_BYTES;
+            const uint32_t b_addr = b_base_u32 + (uint32_t)tap * tap_bytes;
+#pragma unroll
+            for (int k = 0; k < KCHUNK / 16; ++k)
+              umma_f16_warp(d_addr, kmajor_desc(hi_a, a_tap + k * 32), kmajor_desc(hi_b, b_addr + k * 32), idesc,
+                            (tap > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_warp(&a_empty[as]);
+          if (++as == NA) { as = 0; aphase ^= 1; }
+        }
+        umma_commit_warp(&tmem_full[buf]);
+      } else {
+        // order (chunk, tap, tile g): every streamed weight tile is used by all G tiles of the round
+        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+          {
+            int s = as;
+            uint32_t ph = aphase;
+            for (int g = 0; g < gcount; ++g) {
+              mbar_wait(&a_full[s], ph);
+              if (++s == NA) { s = 0; ph ^= 1; }
+            }
+          }
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_full[bs], bphase);
+            tc_fence_after();
+            const uint32_t b_addr = b_base_u32 + (uint32_t)bs * tap_bytes;
+            const uint32_t tap_off = (uint32_t)((tap / 3) * p.pitch + (tap % 3)) * ROW_BYTES;
+            int s = as;
+            for (int g = 0; g < gcount; ++g) {
+              const uint32_t a_tap = a_base_u32 + (uint32_t)s * a_slot + tap_off;
+              const uint32_t d_addr = tmem_d + (uint32_t)g * n_tile;
+#pragma unroll
+              for (int k = 0; k < KCHUNK / 16; ++k)
+                umma_f16_warp(d_addr, kmajor_desc(hi_a, a_tap + k * 32), kmajor_desc(hi_b, b_addr + k * 32), idesc,
+                              (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              if (++s == NA) s = 0;
+            }
+            umma_commit_warp(&b_empty[bs]);
+            if (++bs == p.stages) { bs = 0; bphase ^= 1; }
+          }
+          for (int g = 0; g < gcount; ++g) {
+            umma_commit_warp(&a_empty[as]);
+            if (++as == NA) { as = 0; aphase ^= 1; }
+          }
+        }
+        umma_commit_warp(&tmem_full[buf]);
+      }
+    }
+  } else {
+    // ================================ epilogue: two groups of 4 warps =============
+    const int grp = (warp - 2) >> 2;         // group g owns TMEM buffer g and the rounds with (it & 1) == g
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const int etid = ((warp - 2) & 3) * 32 + lane;
+    const int w_l = row & (kHaloTW - 1), h_l = row >> 3;
+    const float nw = p.noise_w ? __ldg(p.noise_w) : 0.f;
+    TableEntry* my_table = table + grp * 256;
+    int cached_bt = -1, cached_nt = -1;
+    int it = 0;
+    uint32_t use = 0;
+    for (int w = blockIdx.x; w < p.num_tiles; w += gridDim.x, ++it) {
+      if ((it & 1) != grp) continue;
+      const int nt = w % p.num_n_tiles, m0 = (w / p.num_n_tiles) * G;
+      const int gcount = min(G, p.num_m_tiles - m0);
+      const int n0 = nt * p.n_tile;
+      MTile tc = decode_mtile(p, m0);
+      float4 nz_next = load_noise(p, tc.bt, tc.y0 + h_l, tc.x0 + w_l, nw);   // overlaps the MMAs of this round
+      mbar_wait(&tmem_full[grp], use & 1);
+      ++use;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * 256);
+      for (int g = 0; g < gcount; ++g) {
+        const float4 nz = nz_next;
+        const MTile cur = tc;
+        if (g + 1 < gcount) {
+          tc = decode_mtile(p, m0 + g + 1);
+          nz_next = load_noise(p, tc.bt, tc.y0 + h_l, tc.x0 + w_l, nw);
+        }
+        if (cur.bt != cached_bt || nt != cached_nt) {
+          named_bar_sync(1 + grp, 128);
+          fill_table(p, my_table, etid, cur.bt, n0);
+          named_bar_sync(1 + grp, 128);
+          cached_bt = cur.bt; cached_nt = nt;
+        }
+        epilogue_tile<DT>(p, my_table, taddr + (uint32_t)(g * p.n_tile), g == gcount - 1 ? &tmem_empty[grp] : nullptr,
+                          n0, nt, cur.bt, cur.y0 + h_l, cur.x0 + w_l, true, nz);
+      }
     }
   }
 
@@ -284,17 +570,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 int conv_up_nc(int Cout) { return Cout < 32 ? Cout : 32; }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 int conv_plan(const ConvLaunch& a, ConvPlan* p) {
   HF_REQUIRE(a.B > 0 && a.H > 0 && a.W > 0, "conv: bad shape B=%d H=%d W=%d", a.B, a.H, a.W);
   HF_REQUIRE(a.taps == 9 || a.taps == 1, "conv: taps must be 9 or 1");
   HF_REQUIRE(a.Cin % 32 == 0 && a.Cin >= 32, "conv: Cin=%d must be a multiple of 32", a.Cin);
   HF_REQUIRE(a.Cout % 32 == 0 && a.Cout >= 32, "conv: Cout=%d must be a multiple of 32", a.Cout);
   HF_REQUIRE(!a.up || a.taps == 9, "conv: upsample needs a 3x3 kernel");
-  p->TW = a.W < 16 ? a.W : 16;
-  HF_REQUIRE(128 % p->TW == 0, "conv: width %d unsupported (tile width must divide 128)", a.W);
-  p->TH = a.H < 128 / p->TW ? a.H : 128 / p->TW;
-  HF_REQUIRE(128 % (p->TW * p->TH) == 0, "conv: %dx%d image does not tile into 128 GEMM rows", a.H, a.W);
-  p->TB = 128 / (p->TW * p->TH);
+  p->halo = (a.taps == 9 && a.H % kHaloTH == 0 && a.W % kHaloTW == 0 && !env_int("HF_CONV_V1", 0)) ? 1 : 0;
+  p->G = 1; p->na_slots = 0; p->pitch = 0; p->b_resident = 0; p->a_slot_bytes = 0;
+  if (p->halo) {
+    p->TW = kHaloTW; p->TH = kHaloTH; p->TB = 1;
+  } else {
+    p->TW = a.W < 16 ? a.W : 16;
+    HF_REQUIRE(128 % p->TW == 0, "conv: width %d unsupported (tile width must divide 128)", a.W);
+    p->TH = a.H < 128 / p->TW ? a.H : 128 / p->TW;
+    HF_REQUIRE(128 % (p->TW * p->TH) == 0, "conv: %dx%d image does not tile into 128 GEMM rows", a.H, a.W);
+    p->TB = 128 / (p->TW * p->TH);
+  }
   HF_REQUIRE(a.W % p->TW == 0 && a.H % p->TH == 0, "conv: %dx%d not divisible by tile %dx%d", a.H, a.W, p->TH, p->TW);
   p->tiles_x = a.W / p->TW;
   p->tiles_y = a.H / p->TH;
@@ -304,45 +601,84 @@ int conv_plan(const ConvLaunch& a, ConvPlan* p) {
   const int ntot = a.up ? 4 * a.Cout : a.Cout;
   const int nmin = a.up ? 128 : 32;
   const int sms = num_sms();
+  const int table_cap = p->halo ? 256 : 512;       // entries per epilogue group
   int n_tile = 0;
   if (a.force_n_tile) {
     n_tile = a.force_n_tile;
   } else {
     for (int cand = 256; cand >= nmin; cand >>= 1) {
-      if (ntot % cand || p->TB * (a.up ? cand / 4 : cand) > 512) continue;
+      if (ntot % cand || p->TB * (a.up ? cand / 4 : cand) > table_cap) continue;
       n_tile = cand;
       if ((int64_t)p->num_m_tiles * (ntot / cand) >= sms) break;   // largest tile that still fills the GPU
     }
   }
   HF_REQUIRE(n_tile >= nmin && n_tile <= 256 && ntot % n_tile == 0 && n_tile % 32 == 0 &&
-                 p->TB * (a.up ? n_tile / 4 : n_tile) <= 512,
+                 p->TB * (a.up ? n_tile / 4 : n_tile) <= table_cap,
              "conv: no valid N tile (Ntot=%d, n_tile=%d, TB=%d)", ntot, n_tile, p->TB);
   p->n_tile = n_tile;
   p->num_n_tiles = ntot / n_tile;
   p->nc = a.up ? n_tile / 4 : n_tile;
-  const size_t stage_bytes = (size_t)128 * p->kchunk * 2 + (size_t)n_tile * p->kchunk * 2;
   const size_t fixed = 1024 /*align*/ + kTableBytes + 512 /*barriers*/;
-  int stages = (int)((232448 - fixed) / stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  HF_REQUIRE(stages >= 2, "conv: not enough shared memory for 2 stages");
-  p->stages = stages;
-  p->smem_bytes = fixed + stages * stage_bytes;
-  p->num_tiles = p->num_m_tiles * p->num_n_tiles;
+  const size_t budget = 232448 - fixed;
+  const int row_bytes = p->kchunk * 2;
+  if (p->halo) {
+    // rounds: G tiles share one 256-column accumulator buffer; keep at least one round per SM
+    int G = 1;
+    const int gmax = env_int("HF_HALO_GMAX", kMaxG);
+    while (G * 2 <= gmax && G * 2 * n_tile <= 256 &&
+           (int64_t)(p->num_m_tiles / (G * 2)) * p->num_n_tiles >= sms)
+      G *= 2;
+    p->G = G;
+    p->pitch = env_int("HF_HALO_PITCH", 10);
+    HF_REQUIRE(p->pitch == 10 || p->pitch == 16, "conv: HF_HALO_PITCH must be 10 or 16");
+    p->a_slot_bytes = (uint32_t)(((size_t)kHaloRows * p->pitch * row_bytes + 1023) & ~size_t(1023));
+    const size_t tap_bytes = (size_t)n_tile * row_bytes;
+    const int kc = a.Cin / p->kchunk;
+    p->b_resident = (kc == 1 && p->num_n_tiles == 1 && 9 * tap_bytes + 2 * (size_t)p->a_slot_bytes <= budget &&
+                     env_int("HF_HALO_RESIDENT", 1))
+                        ? 1 : 0;
+    if (p->b_resident) {
+      int na = (int)((budget - 9 * tap_bytes) / p->a_slot_bytes);
+      p->na_slots = na > kMaxASlots ? kMaxASlots : na;
+      p->stages = 1;
+      p->smem_bytes = fixed + 9 * tap_bytes + (size_t)p->na_slots * p->a_slot_bytes;
+    } else {
+      // A ring: 2G slots if they fit next to >= 3 weight stages, else G
+      int na = 2 * G;
+      if ((size_t)na * p->a_slot_bytes + 3 * tap_bytes > budget) na = G;
+      if (na > kMaxASlots) na = kMaxASlots;
+      if (na < 2) na = 2;
+      HF_REQUIRE(na >= G, "conv: halo ring too small for G=%d", G);
+      int stages = (int)((budget - (size_t)na * p->a_slot_bytes) / tap_bytes);
+      if (stages > kMaxStages) stages = kMaxStages;
+      HF_REQUIRE(stages >= 2, "conv: not enough shared memory for 2 weight stages");
+      // spend what is left on more halo slots
+      while (na < kMaxASlots && (size_t)(na + 1) * p->a_slot_bytes + (size_t)stages * tap_bytes <= budget) ++na;
+      p->na_slots = na;
+      p->stages = stages;
+      p->smem_bytes = fixed + (size_t)na * p->a_slot_bytes + (size_t)stages * tap_bytes;
+    }
+    const int rounds = (p->num_m_tiles + G - 1) / G;
+    p->num_tiles = rounds * p->num_n_tiles;
+  } else {
+    const size_t stage_bytes = (size_t)128 * row_bytes + (size_t)n_tile * row_bytes;
+    int stages = (int)(budget / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    HF_REQUIRE(stages >= 2, "conv: not enough shared memory for 2 stages");
+    p->stages = stages;
+    p->smem_bytes = fixed + stages * stage_bytes;
+    p->num_tiles = p->num_m_tiles * p->num_n_tiles;
+  }
   p->grid = p->num_tiles < sms ? p->num_tiles : sms;
   return HF_OK;
 }
 
-template <int KCHUNK, int DT>
-static int launch_conv_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& kp,
-                         const ConvPlan& pl, cudaStream_t st) {
-  static bool attr_set = false;
-  auto kern = conv_igemm_kernel<KCHUNK, DT>;
-  if (!attr_set) {
-    HF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
-  }
-  kern<<<pl.grid, kConvThreads, pl.smem_bytes, st>>>(tmA, tmB, kp);
-  HF_LAUNCH_OK("conv_igemm");
+template <typename K>
+static int launch_kernel(K kern, int threads, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                         const ConvKernelParams& kp, const ConvPlan& pl, cudaStream_t st, const char* name) {
+  HF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  kern<<<pl.grid, threads, pl.smem_bytes, st>>>(tmA, tmB, kp);
+  HF_LAUNCH_OK(name);
   count_launch();
   return HF_OK;
 }
@@ -362,6 +698,7 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st, ConvPlan* plan_out) {
     uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
     uint64_t strides[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.W * a.Cin * 2, (uint64_t)a.H * a.W * a.Cin * 2};
     uint32_t box[4] = {(uint32_t)pl.kchunk, (uint32_t)pl.TW, (uint32_t)pl.TH, (uint32_t)pl.TB};
+    if (pl.halo) { box[1] = (uint32_t)pl.pitch; box[2] = kHaloRows; box[3] = 1; }
     rc = encode_tmap(&tmA, a.dtype, 4, const_cast<void*>(a.xhat_in), dims, strides, box, pl.kchunk * 2);
     if (rc) return rc;
   }
@@ -382,12 +719,15 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st, ConvPlan* plan_out) {
   kp.taps = a.taps; kp.up = a.up; kp.act = a.act;
   kp.TW = pl.TW; kp.TH = pl.TH; kp.TB = pl.TB; kp.tiles_x = pl.tiles_x; kp.tiles_y = pl.tiles_y;
   kp.n_tile = pl.n_tile; kp.num_n_tiles = pl.num_n_tiles; kp.num_tiles = pl.num_tiles;
+  kp.num_m_tiles = pl.num_m_tiles;
   kp.kc_per_tap = a.Cin / pl.kchunk;
   kp.num_kb = a.taps * kp.kc_per_tap;
   kp.stages = pl.stages;
   kp.a_bytes = 128u * pl.kchunk * 2;
   kp.stage_bytes = kp.a_bytes + (uint32_t)pl.n_tile * pl.kchunk * 2;
   kp.idesc = make_idesc_f16(a.dtype, 128, pl.n_tile);
+  kp.G = pl.G; kp.na_slots = pl.na_slots; kp.pitch = pl.pitch; kp.b_resident = pl.b_resident;
+  kp.a_slot_bytes = pl.a_slot_bytes;
   kp.d = a.d;
   kp.noise = a.noise;
   kp.noise_bstride = (a.noise && a.noise_batch > 1) ? (int64_t)kp.Ho * kp.Wo : 0;
@@ -401,12 +741,19 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st, ConvPlan* plan_out) {
   kp.rgb_partial = a.rgb_partial;
   if (plan_out) *plan_out = pl;
 
-  if (pl.kchunk == 64) {
-    return a.dtype == HF_BF16 ? launch_conv_t<64, HF_BF16>(tmA, tmB, kp, pl, st)
-                              : launch_conv_t<64, HF_F16>(tmA, tmB, kp, pl, st);
+  const bool bf = a.dtype == HF_BF16;
+  if (pl.halo) {
+    if (pl.kchunk == 64)
+      return bf ? launch_kernel(conv_halo_kernel<64, HF_BF16>, kHaloThreads, tmA, tmB, kp, pl, st, "conv_halo")
+                : launch_kernel(conv_halo_kernel<64, HF_F16>, kHaloThreads, tmA, tmB, kp, pl, st, "conv_halo");
+    return bf ? launch_kernel(conv_halo_kernel<32, HF_BF16>, kHaloThreads, tmA, tmB, kp, pl, st, "conv_halo")
+              : launch_kernel(conv_halo_kernel<32, HF_F16>, kHaloThreads, tmA, tmB, kp, pl, st, "conv_halo");
   }
-  return a.dtype == HF_BF16 ? launch_conv_t<32, HF_BF16>(tmA, tmB, kp, pl, st)
-                            : launch_conv_t<32, HF_F16>(tmA, tmB, kp, pl, st);
+  if (pl.kchunk == 64)
+    return bf ? launch_kernel(conv_igemm_kernel<64, HF_BF16>, kConvThreads, tmA, tmB, kp, pl, st, "conv_igemm")
+              : launch_kernel(conv_igemm_kernel<64, HF_F16>, kConvThreads, tmA, tmB, kp, pl, st, "conv_igemm");
+  return bf ? launch_kernel(conv_igemm_kernel<32, HF_BF16>, kConvThreads, tmA, tmB, kp, pl, st, "conv_igemm")
+            : launch_kernel(conv_igemm_kernel<32, HF_F16>, kConvThreads, tmA, tmB, kp, pl, st, "conv_igemm");
 }
 
 }  // namespace hf

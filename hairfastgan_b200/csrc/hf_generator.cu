@@ -4,7 +4,10 @@
 // first executed conv, then per layer {up-conv, conv, rgb_combine}.  Every conv epilogue applies
 // demod + noise + bias + leaky-relu, multiplies by the NEXT conv's style scale while casting to the
 // 16-bit NHWC activation, and (for the second conv of a layer) accumulates the ToRGB 1x1 conv.
+#include <stdlib.h>
 #include <string.h>
+
+#include <vector>
 
 #include "hf_kernels.cuh"
 
@@ -129,6 +132,36 @@ static void make_ws(const GenLayout& L, int B, int size, WsLayout* W) {
 }  // namespace hf
 
 using namespace hf;
+
+// Optional per-launch timing of the chain (HF_GEN_PROFILE=1): CUDA events around every conv / rgb_combine
+// launch, printed to stderr after a stream sync.  Diagnostic only; off by default.
+namespace {
+struct ProfRec { char name[16]; int idx, cin, cout, res, up, ntile, halo; cudaEvent_t e0, e1; };
+thread_local std::vector<ProfRec> g_prof;
+thread_local cudaEvent_t g_prof_e0;
+bool prof_on() { static int on = -1; if (on < 0) { const char* v = getenv("HF_GEN_PROFILE"); on = (v && atoi(v)) ? 1 : 0; } return on == 1; }
+void prof_begin(cudaStream_t st) { if (!prof_on()) return; cudaEventCreate(&g_prof_e0); cudaEventRecord(g_prof_e0, st); }
+void prof_end(cudaStream_t st, const char* name, int idx, int cin, int cout, int res, int up, int ntile, int halo) {
+  if (!prof_on()) return;
+  ProfRec r; snprintf(r.name, sizeof(r.name), "%s", name);
+  r.idx = idx; r.cin = cin; r.cout = cout; r.res = res; r.up = up; r.ntile = ntile; r.halo = halo; r.e0 = g_prof_e0;
+  cudaEventCreate(&r.e1); cudaEventRecord(r.e1, st); g_prof.push_back(r);
+}
+void prof_flush(cudaStream_t st, int B) {
+  if (!prof_on()) return;
+  cudaStreamSynchronize(st);
+  float total = 0.f;
+  for (auto& r : g_prof) {
+    float ms = 0.f; cudaEventElapsedTime(&ms, r.e0, r.e1); total += ms;
+    double gf = (strcmp(r.name, "conv") == 0) ? 2.0 * r.cin * r.cout * 9.0 * r.res * r.res * B * 1e-9 : 0.0;
+    fprintf(stderr, "[hf_prof] %-12s #%-2d %4d->%-4d r_in=%-4d up=%d n_tile=%-3d halo=%d  %8.1f us  %7.1f TFLOP/s(alg)\n",
+            r.name, r.idx, r.cin, r.cout, r.res, r.up, r.ntile, r.halo, ms * 1e3, gf / (ms * 1e-3) * 1e-3);
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  fprintf(stderr, "[hf_prof] B=%d sum of timed launches %.1f us\n", B, total * 1e3);
+  g_prof.clear();
+}
+}  // namespace
 
 extern "C" {
 
@@ -278,14 +311,19 @@ int hf_generator_forward(const hf_gen_config* cfg, const void* packed, const hf_
       cl.rgb_w = F(L.rgb[rgb_k].w1); cl.rgb_s = WF(W.s_rgb[rgb_k]); cl.rgb_partial = WF(W.partial);
     }
     ConvPlan pl;
+    prof_begin(st);
     int r = launch_conv(cl, st, &pl);
+    prof_end(st, "conv", i, s.cin, s.cout, s.res_in, s.up, pl.n_tile, pl.halo);
     if (num_nt) *num_nt = pl.num_n_tiles;
     return r;
   };
   auto combine = [&](int k, int num_nt, const float* skip_in, float* dst) -> int {
     const RgbL& r = L.rgb[k];
-    return launch_rgb_combine(WF(W.partial), num_nt, F(r.bias), skip_in, skip_in ? F(r.upk) : nullptr, dst, B, r.res,
-                              r.res, st);
+    prof_begin(st);
+    int rr = launch_rgb_combine(WF(W.partial), num_nt, F(r.bias), skip_in, skip_in ? F(r.upk) : nullptr, dst, B,
+                                r.res, r.res, st);
+    prof_end(st, "rgb_combine", k, r.cin, 3, r.res, 0, num_nt, 0);
+    return rr;
   };
   auto rgb_dst = [&](int k) -> float* {
     if (k == last) return io->out_rgb;
@@ -332,6 +370,7 @@ int hf_generator_forward(const hf_gen_config* cfg, const void* packed, const hf_
     if ((rc = combine(k, nt, skip, dst))) return rc;
     skip = dst;
   }
+  prof_flush(st, B);
   return HF_OK;
 }
 

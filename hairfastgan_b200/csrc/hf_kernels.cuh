@@ -77,6 +77,11 @@ struct ConvLaunch {
   int force_n_tile;       // 0 = auto
 };
 struct ConvPlan {
+  int halo;               // 1: conv_halo_kernel (halo tile in smem, shifted descriptors); 0: conv_igemm_kernel
+  int G;                  // halo: tiles per round (share one accumulator buffer and each weight tile)
+  int na_slots, pitch;    // halo: ring slots, halo row pitch in pixels
+  int b_resident;         // halo: whole weight matrix stays in smem
+  uint32_t a_slot_bytes;
   int TW, TH, TB;         // pixel tile: TW*TH*TB = 128 GEMM rows
   int tiles_x, tiles_y, tiles_b, num_m_tiles;
   int n_tile, num_n_tiles, nc;

@@ -420,11 +420,74 @@ __global__ void __launch_bounds__(256) rgb_combine_kernel(const float* partial, 
   }
 }
 
+// W % 4 == 0: four consecutive outputs per thread, float4 partial loads / stores; the 2x2-tap up-FIR of the
+// skip reads a 2x4 window of the half-resolution image (columns 2q-1 .. 2q+2 for outputs 4q .. 4q+3).
+__global__ void __launch_bounds__(256) rgb_combine_vec4_kernel(const float* partial, int num_partials,
+                                                               int64_t partial_stride,
+                                                               const float* __restrict__ bias,
+                                                               const float* __restrict__ skip,
+                                                               const float* __restrict__ upk, float* rgb, int H, int W,
+                                                               int64_t total4) {
+  __shared__ float kf[16];
+  if (threadIdx.x < 16) kf[threadIdx.x] = upk ? upk[15 - threadIdx.x] : 0.f;
+  __syncthreads();
+  const int h2 = H >> 1, w2 = W >> 1, wq = W >> 2;
+  for (int64_t i4 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i4 < total4;
+       i4 += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i4 % wq);
+    const int64_t t = i4 / wq;
+    const int Y = (int)(t % H);
+    const int plane = (int)(t / H);
+    const float bv = bias ? __ldg(bias + plane % 3) : 0.f;
+    float acc[4] = {bv, bv, bv, bv};
+    for (int s = 0; s < num_partials; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(partial + s * partial_stride + i4 * 4);   // may alias rgb
+      acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+    }
+    if (skip) {
+      const float* sp = skip + (size_t)plane * h2 * w2;
+      const int ky0 = Y & 1;
+      float up[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int ky = ky0 + 2 * a;
+        const int uy = Y + ky - 2;
+        const int iy = uy >> 1;
+        if (uy < 0 || iy >= h2) continue;
+        const float* row = sp + (size_t)iy * w2;
+        float c[4];                                      // columns 2q-1 .. 2q+2
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int ix = 2 * q - 1 + m;
+          c[m] = (ix >= 0 && ix < w2) ? __ldg(row + ix) : 0.f;
+        }
+        // even X (4q, 4q+2): taps kx 0,2 on columns (X/2-1, X/2); odd X: taps kx 1,3 on ((X-1)/2, (X+1)/2)
+        up[0] = fmaf(c[0], kf[ky * 4 + 0], fmaf(c[1], kf[ky * 4 + 2], up[0]));
+        up[1] = fmaf(c[1], kf[ky * 4 + 1], fmaf(c[2], kf[ky * 4 + 3], up[1]));
+        up[2] = fmaf(c[1], kf[ky * 4 + 0], fmaf(c[2], kf[ky * 4 + 2], up[2]));
+        up[3] = fmaf(c[2], kf[ky * 4 + 1], fmaf(c[3], kf[ky * 4 + 3], up[3]));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] += up[j];
+    }
+    *reinterpret_cast<float4*>(rgb + i4 * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
 int launch_rgb_combine(const float* partial, int num_partials, const float* bias, const float* skip,
                        const float* up_kernel, float* rgb, int B, int H, int W, cudaStream_t st) {
   HF_REQUIRE(rgb && (partial || num_partials == 0), "rgb_combine: null pointer");
   HF_REQUIRE(!skip || up_kernel, "rgb_combine: skip given without an upsample kernel");
   int64_t total = (int64_t)B * 3 * H * W;
+  if (W % 4 == 0 && ((((uintptr_t)partial | (uintptr_t)rgb) & 15) == 0)) {
+    int64_t total4 = total / 4;
+    int grid = (int)std::min<int64_t>((total4 + 255) / 256, (int64_t)num_sms() * 16);
+    rgb_combine_vec4_kernel<<<grid, 256, 0, st>>>(partial, num_partials, total, bias, skip, up_kernel, rgb, H, W,
+                                                  total4);
+    HF_LAUNCH_OK("rgb_combine");
+    count_launch();
+    return HF_OK;
+  }
   int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
   rgb_combine_kernel<<<grid, 256, 0, st>>>(partial, num_partials, total, bias, skip, up_kernel, rgb, H, W, total);
   HF_LAUNCH_OK("rgb_combine");

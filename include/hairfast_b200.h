@@ -104,6 +104,11 @@ typedef struct {
 
 size_t hf_conv_workspace_bytes(const hf_conv_desc* d, int batch, int height, int width);
 
+/* Introspection (tests / DESIGN tables; needs no device): the tiling the library will use for this
+ * conv.  out[12] = {halo kernel?, n_tile, num_n_tiles, tiles per round G, halo ring slots, halo pitch,
+ * weights resident?, pipeline stages, dynamic smem bytes, work items, grid, channels per K chunk}. */
+int hf_conv_plan_query(const hf_conv_desc* d, int batch, int height, int width, int* out /* host[12] */);
+
 /* Replaces ModulatedConv2d.forward (model.py:238-279) / StyledConv.forward (model.py:337-343). */
 int hf_conv_forward(const hf_conv_desc* d, const void* packed, const hf_conv_io* io, void* stream);
 

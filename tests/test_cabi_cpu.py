@@ -113,3 +113,28 @@ def test_install_overlay_redirects_reference_imports():
     finally:
         inst.uninstall()
     assert "models.stylegan2.op" not in sys.modules
+
+
+def test_conv_plans_for_every_generator_layer(lib):
+    """Tiling decisions for the 17 StyledConvs of the 1024^2 generator (no device needed): shared memory
+    fits the 227 KB opt-in limit, 4^2/8^2 use the per-tap kernel, everything else the halo kernel, the three
+    single-chunk high-resolution layers keep their weights resident and run in rounds of G tiles."""
+    h = lib.lib()
+    layers = [(512, 512, 4, 0), (512, 512, 4, 1), (512, 512, 8, 0), (512, 512, 8, 1), (512, 512, 16, 0),
+              (512, 512, 16, 1), (512, 512, 32, 0), (512, 512, 32, 1), (512, 512, 64, 0), (512, 256, 64, 1),
+              (256, 256, 128, 0), (256, 128, 128, 1), (128, 128, 256, 0), (128, 64, 256, 1), (64, 64, 512, 0),
+              (64, 32, 512, 1), (32, 32, 1024, 0)]
+    for batch in (1, 3, 4, 12):
+        for i, (cin, cout, r, up) in enumerate(layers):
+            d = lib.hf_conv_desc(cin, cout, 3, up, lib.HF_BF16)
+            out = (C.c_int * 12)()
+            assert h.hf_conv_plan_query(C.byref(d), batch, r, r, out) == 0, h.hf_last_error()
+            halo, n_tile, n_n, G, na, pitch, res, stages, smem, work, grid, kchunk = list(out)
+            assert smem <= 232448 and stages >= 1 and grid <= 148 and work >= 1
+            assert halo == (1 if r >= 16 else 0)
+            assert n_tile * n_n == (4 * cout if up else cout) and G * n_tile <= 256
+            assert kchunk == (32 if cin == 32 else 64)
+            if halo:
+                assert na >= max(2, G) and pitch in (10, 16)
+            if batch == 4 and i in (14, 15, 16):
+                assert res == 1 and G == {14: 4, 15: 2, 16: 8}[i]
