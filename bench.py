@@ -216,7 +216,7 @@ def time_dominant_kernel(gen, dev):
     flops = 2.0 * 512 * 512 * 9 * 64 * 64 * B
     achieved = flops / (ms.value * 1e-3) / 1e12
     pk = peaks()
-    return {"kernel": "conv_igemm_kernel<64,bf16> 512->512 3x3 @64^2 B=4 (+fp32 NCHW store)", "bound": "tensor",
+    return {"kernel": "conv_halo_kernel<64,bf16> 512->512 3x3 @64^2 B=4 (+fp32 NCHW store)", "bound": "tensor",
             "achieved": round(achieved, 1), "peak": pk["tf_burst"], "unit": "TFLOP/s",
             "frac": round(achieved / pk["tf_burst"], 4), "peak_source": pk["src"] + " burst (kernel timed alone)",
             "launch_ms": round(ms.value, 4), "traffic": None}

@@ -196,6 +196,86 @@ __device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
       ::"r"(smem_u32(bar))
       : "memory");
 }
+// All NK (= channels-per-chunk / 16) MMAs of one conv tap in ONE asm block: a single elect, descriptor low
+// words advanced by 2 (= 32 bytes = 16 K-elements) inside PTX.  a_lo/b_lo are descriptor low words
+// ((addr >> 4) | LBO), a_hi/b_hi the loop-invariant high words.  acc_first = 0 zero-initialises the
+// accumulator on the first MMA only.
+template <int NK>
+__device__ __forceinline__ void umma_tap_warp(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                              uint32_t b_hi, uint32_t idesc, uint32_t acc_first) {
+  static_assert(NK == 2 || NK == 4, "NK must be 2 or 4");
+  if (NK == 4) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "add.u32 al, %1, 2;\n\tadd.u32 bl, %3, 2;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
+        "add.u32 al, %1, 4;\n\tadd.u32 bl, %3, 4;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
+        "add.u32 al, %1, 6;\n\tadd.u32 bl, %3, 6;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "add.u32 al, %1, 2;\n\tadd.u32 bl, %3, 2;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first)
+        : "memory");
+  }
+}
+// Single-thread forms, to be used inside `if (elect_one()) { ... }` (CUTLASS style: the whole MMA main loop
+// runs in ONE elected lane, so ptxas needs neither waterfall loops nor per-instruction elect/vote).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+template <int NK>
+__device__ __forceinline__ void umma_tap(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t acc_first) {
+  static_assert(NK == 2 || NK == 4, "NK must be 2 or 4");
+  if (NK == 4) {
+    asm volatile(
+        "{\n\t.reg .pred p, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "add.u32 al, %1, 2;\n\tadd.u32 bl, %3, 2;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
+        "add.u32 al, %1, 4;\n\tadd.u32 bl, %3, 4;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
+        "add.u32 al, %1, 6;\n\tadd.u32 bl, %3, 6;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "add.u32 al, %1, 2;\n\tadd.u32 bl, %3, 2;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first)
+        : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t kmajor_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
+}
 // High 32 bits of a K-major descriptor (SBO, version, layout); the low word is (addr >> 4) | LBO.
 __device__ __forceinline__ uint32_t kmajor_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
   return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | ((layout_type & 7) << 29);

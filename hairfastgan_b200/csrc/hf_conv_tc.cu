@@ -268,7 +268,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    // (whole warp, uniform control flow; one lane is elected inside umma_*_warp)
+    // one elected lane runs the whole main loop (see conv_halo_kernel)
+    if (elect_one()) {
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -287,16 +288,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         {
           const uint32_t a_addr = smem_base_u32 + (uint32_t)stage * p.stage_bytes;
           const uint32_t b_addr = a_addr + p.a_bytes;
-#pragma unroll
-          for (int k = 0; k < KCHUNK / 16; ++k)
-            umma_f16_warp(tmem_d, kmajor_desc(desc_hi, a_addr + k * 32), kmajor_desc(desc_hi, b_addr + k * 32), idesc,
-                          (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit_warp(&empty_bar[stage]);                    // frees the smem slot when the MMAs retire
-          if (kb == p.num_kb - 1) umma_commit_warp(&tmem_full[buf]);   // accumulator ready for the epilogue
+          umma_tap<KCHUNK / 16>(tmem_d, kmajor_desc_lo(a_addr), desc_hi, kmajor_desc_lo(b_addr), desc_hi, idesc,
+                                kb > 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);                    // frees the smem slot when the MMAs retire
+          if (kb == p.num_kb - 1) umma_commit(&tmem_full[buf]);   // accumulator ready for the epilogue
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
+    }  // elect_one
   } else {
     // ================================ epilogue (4 warps) ==========================
     const int wq = warp & 3;                 // TMEM lane quarter this warp may read
@@ -343,6 +343,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 constexpr int kHaloThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 two epilogue groups
 constexpr int kHaloTW = 8, kHaloTH = 16;
 constexpr int kHaloRows = kHaloTH + 2;
+constexpr int kHaloPitch = kHaloTW + 2;   // dense halo rows (pitch 16 measured no faster)
 constexpr int kMaxASlots = 8;
 constexpr int kMaxG = 8;
 
@@ -356,7 +357,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr uint32_t SBO_B = 8 * ROW_BYTES;
   constexpr uint32_t LAYOUT = (KCHUNK == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
   const uint32_t a_slot = p.a_slot_bytes;
-  const uint32_t a_tx = (uint32_t)kHaloRows * p.pitch * ROW_BYTES;     // bytes one halo box delivers
+  const uint32_t a_tx = (uint32_t)kHaloRows * kHaloPitch * ROW_BYTES;     // bytes one halo box delivers
   const uint32_t tap_bytes = (uint32_t)p.n_tile * ROW_BYTES;           // one tap of weights
   const int b_slots = p.b_resident ? 9 : p.stages;
   uint8_t* a_base = smem;                                              // [na_slots][a_slot]
@@ -436,13 +437,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    // (whole warp, uniform control flow; one lane is elected inside umma_*_warp)
+    // CUTLASS style: ONE elected lane runs the whole main loop (waits, MMAs, commits); the other 31 lanes go
+    // straight to the final barrier.  Measured: ~150 issue cycles per UTCHMMA with per-instruction elect.
+    if (elect_one()) {
     int bs = 0, as = 0;
     uint32_t bphase = 0, aphase = 0;
     int it = 0;
-    const uint32_t a_base_u32 = smem_u32(a_base), b_base_u32 = smem_u32(b_base);
-    const uint32_t sbo_a = (uint32_t)p.pitch * ROW_BYTES;            // next 8-pixel group = next halo row
-    const uint32_t hi_a = kmajor_desc_hi(sbo_a, LAYOUT), hi_b = kmajor_desc_hi(SBO_B, LAYOUT);
+    constexpr int NK = KCHUNK / 16;
+    constexpr uint32_t ROW_LO = ROW_BYTES >> 4;                      // one halo pixel row in descriptor units
+    const uint32_t a_base_lo = kmajor_desc_lo(smem_u32(a_base)), b_base_lo = kmajor_desc_lo(smem_u32(b_base));
+    const uint32_t a_slot_lo = a_slot >> 4, tap_lo = tap_bytes >> 4;
+    constexpr uint32_t SBO_A = kHaloPitch * ROW_BYTES;               // next 8-pixel group = next halo row
+    const uint32_t hi_a = kmajor_desc_hi(SBO_A, LAYOUT), hi_b = kmajor_desc_hi(SBO_B, LAYOUT);
     const uint32_t idesc = p.idesc;
     const uint32_t n_tile = (uint32_t)p.n_tile;
     if (p.b_resident) {
@@ -462,21 +468,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int g = 0; g < gcount; ++g) {
           mbar_wait(&a_full[as], aphase);
           tc_fence_after();
-          const uint32_t a_addr = a_base_u32 + (uint32_t)as * a_slot;
+          const uint32_t a_lo = a_base_lo + (uint32_t)as * a_slot_lo;
           const uint32_t d_addr = tmem_d + (uint32_t)g * n_tile;
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t a_tap = a_addr + (uint32_t)((tap / 3) * p.pitch + (tap % 3)) * ROW_BYTES;
-            const uint32_t b_addr = b_base_u32 + (uint32_t)tap * tap_bytes;
-#pragma unroll
-            for (int k = 0; k < KCHUNK / 16; ++k)
-              umma_f16_warp(d_addr, kmajor_desc(hi_a, a_tap + k * 32), kmajor_desc(hi_b, b_addr + k * 32), idesc,
-                            (tap > 0 || k > 0) ? 1u : 0u);
+          // rolled on purpose: the single issuing warp must stay inside the instruction cache
+          // (the fully unrolled form measured ~2x slower: its stalls were all `no_inst`)
+          uint32_t b_lo = b_base_lo;
+#pragma unroll 1
+          for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll 1
+            for (int dx = 0; dx < 3; ++dx) {
+              umma_tap<NK>(d_addr, a_lo + (uint32_t)(dy * kHaloPitch + dx) * ROW_LO, hi_a, b_lo, hi_b, idesc,
+                                (dy | dx) ? 1u : 0u);
+              b_lo += tap_lo;
+            }
           }
-          umma_commit_warp(&a_empty[as]);
+          umma_commit(&a_empty[as]);
           if (++as == NA) { as = 0; aphase ^= 1; }
         }
-        umma_commit_warp(&tmem_full[buf]);
+        umma_commit(&tmem_full[buf]);
       } else {
         // order (chunk, tap, tile g): every streamed weight tile is used by all G tiles of the round
         for (int kc = 0; kc < p.kc_per_tap; ++kc) {
@@ -488,33 +497,32 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (++s == NA) { s = 0; ph ^= 1; }
             }
           }
-#pragma unroll
+#pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_full[bs], bphase);
             tc_fence_after();
-            const uint32_t b_addr = b_base_u32 + (uint32_t)bs * tap_bytes;
-            const uint32_t tap_off = (uint32_t)((tap / 3) * p.pitch + (tap % 3)) * ROW_BYTES;
+            const uint32_t b_lo = b_base_lo + (uint32_t)bs * tap_lo;
+            const int dy = tap / 3;
+            const uint32_t tap_off = (uint32_t)(dy * kHaloPitch + (tap - 3 * dy)) * ROW_LO;
+            const uint32_t acc = (kc > 0 || tap > 0) ? 1u : 0u;
             int s = as;
             for (int g = 0; g < gcount; ++g) {
-              const uint32_t a_tap = a_base_u32 + (uint32_t)s * a_slot + tap_off;
-              const uint32_t d_addr = tmem_d + (uint32_t)g * n_tile;
-#pragma unroll
-              for (int k = 0; k < KCHUNK / 16; ++k)
-                umma_f16_warp(d_addr, kmajor_desc(hi_a, a_tap + k * 32), kmajor_desc(hi_b, b_addr + k * 32), idesc,
-                              (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              umma_tap<NK>(tmem_d + (uint32_t)g * n_tile, a_base_lo + (uint32_t)s * a_slot_lo + tap_off, hi_a, b_lo,
+                                hi_b, idesc, acc);
               if (++s == NA) s = 0;
             }
-            umma_commit_warp(&b_empty[bs]);
+            umma_commit(&b_empty[bs]);
             if (++bs == p.stages) { bs = 0; bphase ^= 1; }
           }
           for (int g = 0; g < gcount; ++g) {
-            umma_commit_warp(&a_empty[as]);
+            umma_commit(&a_empty[as]);
             if (++as == NA) { as = 0; aphase ^= 1; }
           }
         }
-        umma_commit_warp(&tmem_full[buf]);
+        umma_commit(&tmem_full[buf]);
       }
     }
+    }  // elect_one
   } else {
     // ================================ epilogue: two groups of 4 warps =============
     const int grp = (warp - 2) >> 2;         // group g owns TMEM buffer g and the rounds with (it & 1) == g
@@ -629,8 +637,7 @@ int conv_plan(const ConvLaunch& a, ConvPlan* p) {
            (int64_t)(p->num_m_tiles / (G * 2)) * p->num_n_tiles >= sms)
       G *= 2;
     p->G = G;
-    p->pitch = env_int("HF_HALO_PITCH", 10);
-    HF_REQUIRE(p->pitch == 10 || p->pitch == 16, "conv: HF_HALO_PITCH must be 10 or 16");
+    p->pitch = kHaloPitch;
     p->a_slot_bytes = (uint32_t)(((size_t)kHaloRows * p->pitch * row_bytes + 1023) & ~size_t(1023));
     const size_t tap_bytes = (size_t)n_tile * row_bytes;
     const int kc = a.Cin / p->kchunk;
@@ -654,6 +661,8 @@ int conv_plan(const ConvLaunch& a, ConvPlan* p) {
       HF_REQUIRE(stages >= 2, "conv: not enough shared memory for 2 weight stages");
       // spend what is left on more halo slots
       while (na < kMaxASlots && (size_t)(na + 1) * p->a_slot_bytes + (size_t)stages * tap_bytes <= budget) ++na;
+      if (env_int("HF_HALO_NA", 0) >= G) na = env_int("HF_HALO_NA", 0);             // tuning knobs
+      if (env_int("HF_HALO_STAGES", 0) >= 2 && env_int("HF_HALO_STAGES", 0) <= stages) stages = env_int("HF_HALO_STAGES", 0);
       p->na_slots = na;
       p->stages = stages;
       p->smem_bytes = fixed + (size_t)na * p->a_slot_bytes + (size_t)stages * tap_bytes;

@@ -81,4 +81,10 @@ case("styled_64", 64, 64, 16, 3, False, 2, True)          # epilogue: noise/bias
 case("up_64_32", 64, 32, 8, 3, True, 2, False)            # polyphase
 case("up_styled_128_64", 128, 64, 32, 3, True, 1, True)
 case("conv3_32_r64", 32, 32, 64, 3, False, 1, True)       # SW64 + taps
+# halo-kernel modes: resident weights + rounds (G>1), SW64 rounds, streamed weights with G=2, ragged last round
+case("res_g4", 64, 64, 256, 3, False, 2, True)
+case("res_up_g2", 64, 32, 256, 3, True, 1, True)
+case("res_g8_sw64", 32, 32, 512, 3, False, 1, True)
+case("stream_g2", 128, 128, 256, 3, False, 1, True)
+case("stream_up_256", 128, 64, 128, 3, True, 3, True)
 P("done")
