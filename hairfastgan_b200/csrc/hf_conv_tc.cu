@@ -28,6 +28,7 @@
 //    offset; the 128 GEMM rows may span several batch samples (4x4x8, 8x8x2).
 // In both, TMA out-of-bounds zero fill *is* the conv zero padding.
 #include <stdlib.h>
+#include <string.h>
 
 #include "hf_kernels.cuh"
 
@@ -127,7 +128,7 @@ __device__ __forceinline__ float4 load_noise(const ConvKernelParams& p, int b, i
 // TMEM -> registers -> fused epilogue -> global, for one tile and one thread (= one GEMM row = one pixel).
 //   a = acc*d + nw*noise + bias ; a = lrelu(a)*sqrt2 ; rgb += a*wrgb ; out16 = a*s_next
 // `release_bar` != nullptr: arrive on it right after the last TMEM read (hands the accumulator back).
-template <int DT>
+template <int DT, bool REMOTE_RELEASE = false>
 __device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, const TableEntry* trow, uint32_t taddr,
                                               uint64_t* release_bar, int n0, int nt, int b, int y, int x, bool valid,
                                               float4 nz) {
@@ -143,7 +144,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, const T
     tmem_ld_wait();
     if (release_bar && q == chunks - 1) {
       tc_fence_before();
-      mbar_arrive(release_bar);
+      if (REMOTE_RELEASE) mbar_arrive_leader(release_bar); else mbar_arrive(release_bar);
     }
     const int par = p.up ? (q & 3) : 0;
     const int t_base = p.up ? (q >> 2) * 32 : q * 32;          // channel offset inside the tile
@@ -573,6 +574,172 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// =============================================================================================
+// halo kernel, CTA-pair form (cta_group::2) for the wide layers (N tile 256, streamed weights, G = 1):
+// two CTAs of a cluster each own one 8x16-pixel tile (their own halo ring and accumulator) and HALF of the
+// 256-row weight tile; the leader issues M=256 x N=256 x K=16 tcgen05.mma for both.  The ~130-cycle fixed
+// cost that every SS-mode MMA pays (measured, profiles/) is paid once per two tiles, and each CTA pulls
+// only half of the weights through L2 -> smem.
+// =============================================================================================
+template <int DT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kHaloThreads, 1)
+conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const ConvKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int KCHUNK = 64;
+  constexpr uint32_t ROW_BYTES = KCHUNK * 2;
+  constexpr uint32_t ROW_LO = ROW_BYTES >> 4;
+  constexpr uint32_t SBO_A = kHaloPitch * ROW_BYTES, SBO_B = 8 * ROW_BYTES;
+  constexpr uint32_t LAYOUT = UMMA_LAYOUT_SW128;
+  constexpr uint32_t A_TX = kHaloRows * kHaloPitch * ROW_BYTES;
+  constexpr uint32_t B_HALF = 128 * ROW_BYTES;                        // this CTA's half of one weight tap
+  const uint32_t a_slot = p.a_slot_bytes;
+  const int NA = p.na_slots, NS = p.stages;
+  uint8_t* a_base = smem;
+  uint8_t* b_base = smem + (size_t)NA * a_slot;
+  TableEntry* table = reinterpret_cast<TableEntry*>(b_base + (size_t)NS * B_HALF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(table) + kTableBytes);
+  uint64_t* b_full = bars;                          // leader's copies are the ones waited on
+  uint64_t* b_empty = b_full + kMaxStages;
+  uint64_t* a_full = b_empty + kMaxStages;
+  uint64_t* a_empty = a_full + kMaxASlots;
+  uint64_t* tmem_full = a_empty + kMaxASlots;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(&b_full[s], 2);                     // leader's expect_tx arrive + peer's arrive
+      mbar_init(&b_empty[s], 1);                    // leader's multicast commit
+    }
+    for (int i = 0; i < kMaxASlots; ++i) {
+      mbar_init(&a_full[i], 2);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);                  // multicast commit
+      mbar_init(&tmem_empty[i], 256);               // epilogue threads of both CTAs
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_holder, 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  // work item w (per pair): N tile nt, pair round pr -> this CTA's tile = 2*pr + rank
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ====================
+    if (lane == 0) {
+      int bs = 0, as = 0;
+      uint32_t bphase = 0, aphase = 0;
+      for (int w = pair; w < p.num_tiles; w += num_pairs) {
+        const int nt = w % p.num_n_tiles;
+        const MTile tc = decode_mtile(p, 2 * (w / p.num_n_tiles) + (int)rank);
+        const int n0 = nt * 256 + (int)rank * 128;
+        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+          mbar_wait(&a_empty[as], aphase ^ 1);
+          if (leader) mbar_expect_tx(&a_full[as], 2 * A_TX); else mbar_arrive_leader(&a_full[as]);
+          tma2_load_4d(a_base + (size_t)as * a_slot, &tmA, &a_full[as], kc * KCHUNK, tc.x0 - 1, tc.y0 - 1, tc.bt);
+          if (++as == NA) { as = 0; aphase ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_empty[bs], bphase ^ 1);
+            if (leader) mbar_expect_tx(&b_full[bs], 2 * B_HALF); else mbar_arrive_leader(&b_full[bs]);
+            tma2_load_2d(b_base + (size_t)bs * B_HALF, &tmB, &b_full[bs], tap * p.Cin + kc * KCHUNK, n0);
+            if (++bs == NS) { bs = 0; bphase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA, one elected lane) ====
+    if (leader && elect_one()) {
+      int bs = 0, as = 0;
+      uint32_t bphase = 0, aphase = 0;
+      int it = 0;
+      const uint32_t a_base_lo = kmajor_desc_lo(smem_u32(a_base)), b_base_lo = kmajor_desc_lo(smem_u32(b_base));
+      const uint32_t a_slot_lo = a_slot >> 4, b_half_lo = B_HALF >> 4;
+      const uint32_t hi_a = kmajor_desc_hi(SBO_A, LAYOUT), hi_b = kmajor_desc_hi(SBO_B, LAYOUT);
+      const uint32_t idesc = p.idesc;
+      for (int w = pair; w < p.num_tiles; w += num_pairs, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 256);
+        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+          mbar_wait(&a_full[as], aphase);
+          const uint32_t a_lo = a_base_lo + (uint32_t)as * a_slot_lo;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_full[bs], bphase);
+            tc_fence_after();
+            const int dy = tap / 3;
+            umma_tap2_x4(tmem_d, a_lo + (uint32_t)(dy * kHaloPitch + (tap - 3 * dy)) * ROW_LO, hi_a,
+                         b_base_lo + (uint32_t)bs * b_half_lo, hi_b, idesc, (kc > 0 || tap > 0) ? 1u : 0u);
+            umma_commit2(&b_empty[bs]);
+            if (++bs == NS) { bs = 0; bphase ^= 1; }
+          }
+          umma_commit2(&a_empty[as]);
+          if (++as == NA) { as = 0; aphase ^= 1; }
+        }
+        umma_commit2(&tmem_full[buf]);
+      }
+    }
+  } else {
+    // ================================ epilogue: two groups of 4 warps (both CTAs) ==
+    const int grp = (warp - 2) >> 2;
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const int etid = ((warp - 2) & 3) * 32 + lane;
+    const int w_l = row & (kHaloTW - 1), h_l = row >> 3;
+    const float nw = p.noise_w ? __ldg(p.noise_w) : 0.f;
+    TableEntry* my_table = table + grp * 256;
+    int cached_bt = -1, cached_nt = -1;
+    int it = 0;
+    uint32_t use = 0;
+    for (int w = pair; w < p.num_tiles; w += num_pairs, ++it) {
+      if ((it & 1) != grp) continue;
+      const int nt = w % p.num_n_tiles;
+      const MTile tc = decode_mtile(p, 2 * (w / p.num_n_tiles) + (int)rank);
+      const int n0 = nt * 256;
+      const float4 nz = load_noise(p, tc.bt, tc.y0 + h_l, tc.x0 + w_l, nw);
+      if (tc.bt != cached_bt || nt != cached_nt) {
+        named_bar_sync(1 + grp, 128);
+        fill_table(p, my_table, etid, tc.bt, n0);
+        named_bar_sync(1 + grp, 128);
+        cached_bt = tc.bt; cached_nt = nt;
+      }
+      mbar_wait(&tmem_full[grp], use & 1);
+      ++use;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * 256);
+      // hand the accumulator back to the LEADER's barrier (remote arrive from the peer CTA)
+      epilogue_tile<DT, true>(p, my_table, taddr, &tmem_empty[grp], n0, nt, tc.bt, tc.y0 + h_l, tc.x0 + w_l, true, nz);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();       // the peer's smem / TMEM are read by the leader's MMAs until the very end
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -669,6 +836,23 @@ int conv_plan(const ConvLaunch& a, ConvPlan* p) {
     }
     const int rounds = (p->num_m_tiles + G - 1) / G;
     p->num_tiles = rounds * p->num_n_tiles;
+    // CTA-pair form for the wide layers: N tile 256 (128 weight rows per CTA), streamed weights, G = 1
+    if (!p->b_resident && G == 1 && n_tile == 256 && p->kchunk == 64 && p->num_m_tiles % 2 == 0 && sms % 2 == 0 &&
+        env_int("HF_CONV_2CTA", 1)) {
+      p->halo = 2;
+      const size_t half = (size_t)128 * row_bytes;
+      int na = 3;
+      int stages = (int)((budget - (size_t)na * p->a_slot_bytes) / half);
+      if (stages > kMaxStages) stages = kMaxStages;
+      while (na < 4 && (size_t)(na + 1) * p->a_slot_bytes + (size_t)stages * half <= budget) ++na;
+      p->na_slots = na;
+      p->stages = stages;
+      p->smem_bytes = fixed + (size_t)na * p->a_slot_bytes + (size_t)stages * half;
+      p->num_tiles = (p->num_m_tiles / 2) * p->num_n_tiles;          // work items per CTA pair
+      const int pairs = p->num_tiles < sms / 2 ? p->num_tiles : sms / 2;
+      p->grid = 2 * pairs;
+      return HF_OK;
+    }
   } else {
     const size_t stage_bytes = (size_t)128 * row_bytes + (size_t)n_tile * row_bytes;
     int stages = (int)(budget / stage_bytes);
@@ -688,6 +872,27 @@ static int launch_kernel(K kern, int threads, const CUtensorMap& tmA, const CUte
   HF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   kern<<<pl.grid, threads, pl.smem_bytes, st>>>(tmA, tmB, kp);
   HF_LAUNCH_OK(name);
+  count_launch();
+  return HF_OK;
+}
+
+template <typename K>
+static int launch_pair_kernel(K kern, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& kp,
+                              const ConvPlan& pl, cudaStream_t st) {
+  HF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(pl.grid);
+  cfg.blockDim = dim3(kHaloThreads);
+  cfg.dynamicSmemBytes = pl.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  HF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, kp));
+  HF_LAUNCH_OK("conv_halo2");
   count_launch();
   return HF_OK;
 }
@@ -716,7 +921,7 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st, ConvPlan* plan_out) {
     const uint64_t N = a.up ? 4ull * a.Cout : (uint64_t)a.Cout;
     uint64_t dims[2] = {K, N};
     uint64_t strides[1] = {K * 2};
-    uint32_t box[2] = {(uint32_t)pl.kchunk, (uint32_t)pl.n_tile};
+    uint32_t box[2] = {(uint32_t)pl.kchunk, (uint32_t)(pl.halo == 2 ? 128 : pl.n_tile)};
     rc = encode_tmap(&tmB, a.dtype, 2, const_cast<void*>(a.wpk), dims, strides, box, pl.kchunk * 2);
     if (rc) return rc;
   }
@@ -734,7 +939,7 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st, ConvPlan* plan_out) {
   kp.stages = pl.stages;
   kp.a_bytes = 128u * pl.kchunk * 2;
   kp.stage_bytes = kp.a_bytes + (uint32_t)pl.n_tile * pl.kchunk * 2;
-  kp.idesc = make_idesc_f16(a.dtype, 128, pl.n_tile);
+  kp.idesc = make_idesc_f16(a.dtype, pl.halo == 2 ? 256 : 128, pl.n_tile);
   kp.G = pl.G; kp.na_slots = pl.na_slots; kp.pitch = pl.pitch; kp.b_resident = pl.b_resident;
   kp.a_slot_bytes = pl.a_slot_bytes;
   kp.d = a.d;
@@ -751,6 +956,9 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st, ConvPlan* plan_out) {
   if (plan_out) *plan_out = pl;
 
   const bool bf = a.dtype == HF_BF16;
+  if (pl.halo == 2)
+    return bf ? launch_pair_kernel(conv_halo2_kernel<HF_BF16>, tmA, tmB, kp, pl, st)
+              : launch_pair_kernel(conv_halo2_kernel<HF_F16>, tmA, tmB, kp, pl, st);
   if (pl.halo) {
     if (pl.kchunk == 64)
       return bf ? launch_kernel(conv_halo_kernel<64, HF_BF16>, kHaloThreads, tmA, tmB, kp, pl, st, "conv_halo")

@@ -131,10 +131,12 @@ def test_conv_plans_for_every_generator_layer(lib):
             assert h.hf_conv_plan_query(C.byref(d), batch, r, r, out) == 0, h.hf_last_error()
             halo, n_tile, n_n, G, na, pitch, res, stages, smem, work, grid, kchunk = list(out)
             assert smem <= 232448 and stages >= 1 and grid <= 148 and work >= 1
-            assert halo == (1 if r >= 16 else 0)
+            assert (halo in (1, 2)) == (r >= 16)
             assert n_tile * n_n == (4 * cout if up else cout) and G * n_tile <= 256
             assert kchunk == (32 if cin == 32 else 64)
             if halo:
                 assert na >= max(2, G) and pitch in (10, 16)
+            if halo == 2:      # CTA-pair kernel: full 256-wide N tile, one tile per CTA
+                assert n_tile == 256 and G == 1 and res == 0 and grid % 2 == 0
             if batch == 4 and i in (14, 15, 16):
                 assert res == 1 and G == {14: 4, 15: 2, 16: 8}[i]

@@ -87,4 +87,8 @@ case("res_up_g2", 64, 32, 256, 3, True, 1, True)
 case("res_g8_sw64", 32, 32, 512, 3, False, 1, True)
 case("stream_g2", 128, 128, 256, 3, False, 1, True)
 case("stream_up_256", 128, 64, 128, 3, True, 3, True)
+# CTA-pair kernel (cta_group::2): N tile 256, streamed weights
+case("pair_512", 512, 512, 64, 3, False, 4, True)
+case("pair_up_256_128", 256, 128, 64, 3, True, 3, True)
+case("pair_256_b1", 256, 256, 128, 3, False, 1, False)
 P("done")
