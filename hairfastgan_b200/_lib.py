@@ -57,7 +57,8 @@ class hf_gen_io(C.Structure):
                 ("start_layer", C.c_int), ("end_layer", C.c_int),
                 ("layer_in", C.c_void_p), ("skip_in", C.c_void_p),
                 ("out_feature", C.c_void_p), ("out_rgb", C.c_void_p),
-                ("feature_in", C.c_void_p), ("feature_idx", C.c_int), ("feature_alpha", C.c_float)]
+                ("feature_in", C.c_void_p * HF_MAX_STYLED), ("feature_alpha", C.c_float),
+                ("features_out", C.c_void_p * (HF_MAX_STYLED + 1))]
 
 
 # every symbol include/hairfast_b200.h declares: name -> (restype, argtypes)

@@ -237,8 +237,11 @@ int hf_generator_forward(const hf_gen_config* cfg, const void* packed, const hf_
              start, end, n);
   HF_REQUIRE(start == 0 || io->layer_in, "hf_generator_forward: start_layer=%d needs layer_in (model.py:546)", start);
   HF_REQUIRE(!(start > 0 && end == 0), "hf_generator_forward: start_layer>0 with end_layer=0 is not supported");
-  HF_REQUIRE(!io->feature_in || io->feature_alpha == 1.0f,
-             "hf_generator_forward: feature blend supports feature_alpha == 1 only (got %f)", io->feature_alpha);
+  bool any_feat = false;
+  for (int i = 0; i < HF_MAX_STYLED; ++i) any_feat |= (io->feature_in[i] != nullptr);
+  HF_REQUIRE(!any_feat || io->feature_alpha == 1.0f,
+             "hf_generator_forward: insert_feature supports feature_scale == 1 only (got %f)", io->feature_alpha);
+  HF_REQUIRE(!io->feature_in[0], "hf_generator_forward: feature_in[0] is never consumed (model.py insert_feature starts at 1)");
   // Which layers run (mirror of the loop at model.py:541-557)
   bool run[16] = {false};
   run[0] = (start == 0);
@@ -306,7 +309,8 @@ int hf_generator_forward(const hf_gen_config* cfg, const void* packed, const hf_
                io->noise_batch[i]);
     cl.noise = io->noise[i]; cl.noise_batch = io->noise_batch[i]; cl.noise_w = F(s.noise_w);
     cl.bias = F(s.act_bias); cl.act = 1;
-    cl.s_next = s_next; cl.xhat_out = xout; cl.out_nchw = out_nchw;
+    cl.s_next = s_next; cl.xhat_out = xout;
+    cl.out_nchw = io->features_out[i + 1] ? io->features_out[i + 1] : out_nchw;    // return_features
     if (rgb_k >= 0) {
       cl.rgb_w = F(L.rgb[rgb_k].w1); cl.rgb_s = WF(W.s_rgb[rgb_k]); cl.rgb_partial = WF(W.partial);
     }
@@ -331,6 +335,11 @@ int hf_generator_forward(const hf_gen_config* cfg, const void* packed, const hf_
     return WF(W.rgbbuf[rgb_slot]);
   };
 
+  if (io->features_out[0])
+    for (int b = 0; b < B; ++b)
+      if ((rc = launch_scale_copy(F(L.const_in), io->features_out[0] + (size_t)b * L.st[0].cin * 16,
+                                  (int64_t)L.st[0].cin * 16, 1.f, st)))
+        return rc;
   if (run[0]) {
     if ((rc = launch_modulate_to_nhwc(F(L.const_in), 1, WF(W.s_conv[0]), nullptr, 0.f, xb(cur), B, L.st[0].cin, 16,
                                       cfg->dtype, st)))
@@ -350,16 +359,19 @@ int hf_generator_forward(const hf_gen_config* cfg, const void* packed, const hf_
   for (int k = 1; k <= n; ++k) {
     if (!run[k]) continue;
     const int iu = 2 * k - 1, ic = 2 * k;
-    const bool feat_here = io->feature_in && io->feature_idx == iu;
-    if (k == start || feat_here) {
+    if (k == start || io->feature_in[iu]) {
       // layer_in (model.py:546) or the FSE feature insertion (alpha == 1): fresh NCHW fp32 input
-      const float* src = feat_here ? io->feature_in : io->layer_in;
+      const float* src = io->feature_in[iu] ? io->feature_in[iu] : io->layer_in;
       if ((rc = launch_modulate_to_nhwc(src, 0, WF(W.s_conv[iu]), nullptr, 0.f, xb(cur), B, L.st[iu].cin,
                                         L.st[iu].res_in * L.st[iu].res_in, cfg->dtype, st)))
         return rc;
     }
     if ((rc = run_conv(iu, xb(cur), xb(cur ^ 1), WF(W.s_conv[ic]), nullptr, -1, nullptr))) return rc;
     cur ^= 1;
+    if (io->feature_in[ic])      // insert_feature before the second conv of the layer
+      if ((rc = launch_modulate_to_nhwc(io->feature_in[ic], 0, WF(W.s_conv[ic]), nullptr, 0.f, xb(cur), B,
+                                        L.st[ic].cin, L.st[ic].res_in * L.st[ic].res_in, cfg->dtype, st)))
+        return rc;
     const bool more = (k < last);
     int nt = 0;
     if ((rc = run_conv(ic, xb(cur), more ? xb(cur ^ 1) : nullptr, more ? WF(W.s_conv[ic + 1]) : nullptr,

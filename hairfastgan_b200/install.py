@@ -22,6 +22,10 @@ _TARGETS = {
     "models.stylegan2.op.fused_act": "hairfastgan_b200.op.fused_act",
     "models.stylegan2.op.upfirdn2d": "hairfastgan_b200.op.upfirdn2d",
     "models.stylegan2.model": "hairfastgan_b200.model",
+    # FeatureStyleEncoder puts its own directory on sys.path (FSencoder.py:12-13) and imports the generator
+    # copy as `pixel2style2pixel.models.stylegan2.model` (trainer.py:18)
+    "pixel2style2pixel.models.stylegan2.model": "hairfastgan_b200.fse_model",
+    "models.FeatureStyleEncoder.pixel2style2pixel.models.stylegan2.model": "hairfastgan_b200.fse_model",
 }
 
 
@@ -31,6 +35,13 @@ def install(generator: bool = True) -> None:
     for ref_name, ours in _TARGETS.items():
         if ref_name.endswith(".model") and not generator:
             continue
+        if ref_name.startswith("pixel2style2pixel"):
+            # parents of this name only exist once FSencoder.py has extended sys.path; register stubs so the
+            # absolute import resolves without executing the reference copy
+            import types
+            parts = ref_name.split(".")
+            for i in range(1, len(parts)):
+                sys.modules.setdefault(".".join(parts[:i]), types.ModuleType(".".join(parts[:i])))
         sys.modules[ref_name] = importlib.import_module(ours)
 
 

@@ -426,6 +426,14 @@ class Generator(nn.Module):
     def forward(self, styles, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
                 input_is_latent=False, noise=None, randomize_noise=True, layer_in=None, skip=None,
                 start_layer=0, end_layer=8, return_rgb=False):
+        latent = self._build_latent(styles, inject_index, truncation, truncation_latent, input_is_latent)
+        early, out_feat, out_rgb, _ = self._run(latent, noise, randomize_noise, layer_in, skip, start_layer, end_layer)
+        if early:
+            return out_feat, out_rgb
+        return (out_rgb, latent) if return_latents else (out_rgb, None)
+
+    def _build_latent(self, styles, inject_index, truncation, truncation_latent, input_is_latent):
+        """styles -> [B, n_latent, style_dim] exactly as the reference does (model.py:494-531)."""
         if not input_is_latent:
             styles = [self.style(s) for s in styles]
         if truncation < 1:
@@ -438,6 +446,11 @@ class Generator(nn.Module):
                 inject_index = random.randint(1, self.n_latent - 1)
             latent = torch.cat([styles[0].unsqueeze(1).repeat(1, inject_index, 1),
                                 styles[1].unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)], 1)
+        return latent
+
+    def _run(self, latent, noise, randomize_noise, layer_in=None, skip=None, start_layer=0, end_layer=8,
+             features_in=None, feature_scale=1.0, return_features=False):
+        """One hf_generator_forward call.  Returns (early_exit, out_feature, out_rgb, outs)."""
         if not latent.is_cuda:
             raise RuntimeError("Generator: latent must be a CUDA tensor (hairfastgan_b200 has no CPU fallback)")
         device = latent.device
@@ -506,10 +519,31 @@ class Generator(nn.Module):
             out_feat = torch.empty(batch, self.channels[res_last], res_last, res_last, device=device,
                                    dtype=torch.float32)
             io.out_feature = out_feat.data_ptr()
+        # FeatureStyleEncoder generator variant: insert_feature / return_features
+        io.feature_alpha = float(feature_scale)
+        if features_in is not None:
+            for i, f in enumerate(features_in):
+                if f is None or i == 0 or i >= self.num_layers:
+                    continue
+                if float(feature_scale) != 1.0:
+                    raise RuntimeError("Generator: insert_feature is implemented for feature_scale == 1.0 only "
+                                       "(HairFast always runs min(1, 1e-4 * 1e5) = 1.0)")
+                ff = _f32c(f)
+                keep.append(ff)
+                io.feature_in[i] = ff.data_ptr()
+        outs = None
+        if return_features:
+            outs = [torch.empty(batch, self.channels[4], 4, 4, device=device, dtype=torch.float32)]
+            io.features_out[0] = outs[0].data_ptr()
+            for k in range(n_layers + 1):
+                for i in ([0] if k == 0 else [2 * k - 1, 2 * k]):
+                    r = 4 * 2 ** k
+                    t = torch.empty(batch, self.channels[r], r, r, device=device, dtype=torch.float32) if run[k] else None
+                    outs.append(t)
+                    if t is not None:
+                        io.features_out[i + 1] = t.data_ptr()
         ws = self._get_workspace(cfg, batch, device)
         flag = C.c_int(0)
         _lib.check(lib.hf_generator_forward(C.byref(cfg), self._packed.data_ptr(), C.byref(io), ws.data_ptr(),
                                             C.byref(flag), _lib.stream_ptr()), "hf_generator_forward")
-        if early:
-            return out_feat, out_rgb
-        return (out_rgb, latent) if return_latents else (out_rgb, None)
+        return early, out_feat, out_rgb, outs

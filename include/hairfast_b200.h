@@ -172,10 +172,14 @@ typedef struct {
   float* out_feature;    /* early exit: `out` [B,C,R,R] fp32 NCHW (model.py:537-538,550-551) */
   float* out_rgb;        /* image [B,3,size,size], or the early-exit `skip` [B,3,R,R] */
   /* FeatureStyleEncoder generator variant (pixel2style2pixel/models/stylegan2/model.py:527-560):
-   * x = (1-alpha)*x + alpha*feature_in before the conv that consumes latent index feature_idx */
-  const float* feature_in;
-  int feature_idx;
+   * insert_feature: x = (1-alpha)*x + alpha*feature_in[i] before the styled conv that consumes latent
+   * index i (i >= 1; [B,Cin_i,R,R] fp32 NCHW or NULL).  Only alpha == 1 (what HairFast runs:
+   * min(1, 1e-4 * n_iter) with n_iter = 1e5, trainer.py:358-359) is implemented.
+   * return_features: features_out[0] = ConstantInput output, features_out[i+1] = output of styled conv i
+   * ([B,Cout_i,R,R] fp32 NCHW each; NULL entries are skipped). */
+  const float* feature_in[HF_MAX_STYLED];
   float feature_alpha;
+  float* features_out[HF_MAX_STYLED + 1];
 } hf_gen_io;
 
 /* Replaces Generator.forward(styles=[latent], input_is_latent=True, noise=..., layer_in, skip,

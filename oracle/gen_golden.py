@@ -150,6 +150,23 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "generator256.npz"), **out)
     print("generator256.npz", len(out))
 
+    # ---- 4b. FeatureStyleEncoder's generator copy: insert_feature at idx 5 (alpha = 1) + return_features
+    sys.path.insert(0, os.path.join(REF, "models", "FeatureStyleEncoder"))
+    from pixel2style2pixel.models.stylegan2.model import Generator as FSEGenerator
+    fgen = FSEGenerator(size, 512, 8)
+    fgen.load_state_dict(params, strict=True)
+    fgen.eval()
+    fea = torch.randn(2, 512, 16, 16, generator=torch.Generator().manual_seed(6))
+    feats = [None] * 5 + [fea] + [None] * 12
+    fimg, fouts = fgen([lat], input_is_latent=True, noise=noise, return_features=True, features_in=feats,
+                       feature_scale=1.0)
+    np.savez_compressed(os.path.join(GOLD, "generator256_fse.npz"),
+                        image=fimg[:, :, ::4, ::4].numpy(), n_outs=np.int64(len(fouts)),
+                        out0=fouts[0][:, ::64].numpy(), out4=fouts[4][:, ::16].numpy(),
+                        out5=fouts[5][:, ::16].numpy(), out6=fouts[6][:, ::16, ::2, ::2].numpy(),
+                        out_last=fouts[-1][:, ::16, ::8, ::8].numpy())
+    print("generator256_fse.npz", len(fouts))
+
     # ---- 5. full-size 1024^2 generator, B=1 (config 2 shape), subsampled output
     size = 1024
     params = O.synth_generator_params(size=size, seed=0)

@@ -189,6 +189,39 @@ def generator_ref(p: Dict[str, Tensor], latent: Tensor, noise: List[Tensor],
     return skip, None
 
 
+def generator_fse_ref(p: Dict[str, Tensor], latent: Tensor, noise: List[Tensor],
+                      features_in: Optional[List[Optional[Tensor]]] = None, feature_scale: float = 1.0):
+    """FeatureStyleEncoder's generator copy
+    (models/FeatureStyleEncoder/pixel2style2pixel/models/stylegan2/model.py:527-560): full forward with
+    ``insert_feature`` (x = (1-a)*x + a*features_in[idx]) before every styled conv of the layer loop and
+    ``return_features`` (list of the ConstantInput output and every StyledConv output).
+    Returns (image, outs)."""
+    def insert(x, idx):
+        if features_in is not None and features_in[idx] is not None:
+            x = (1 - feature_scale) * x + feature_scale * features_in[idx]
+        return x
+    b = latent.shape[0]
+    outs = []
+    out = p["input.input"].repeat(b, 1, 1, 1)
+    outs.append(out)
+    out = styled_conv_ref(out, latent[:, 0], p, "conv1.", noise[0], False)
+    outs.append(out)
+    skip = to_rgb_ref(out, latent[:, 1], p, "to_rgb1.", None)
+    n_layers = (len(noise) - 1) // 2
+    i = 1
+    for layer in range(1, n_layers + 1):
+        c1, c2, rgb = f"convs.{2 * layer - 2}.", f"convs.{2 * layer - 1}.", f"to_rgbs.{layer - 1}."
+        out = insert(out, i)
+        out = styled_conv_ref(out, latent[:, i], p, c1, noise[2 * layer - 1], True)
+        outs.append(out)
+        out = insert(out, i + 1)
+        out = styled_conv_ref(out, latent[:, i + 1], p, c2, noise[2 * layer], False)
+        outs.append(out)
+        skip = to_rgb_ref(out, latent[:, i + 2], p, rgb, skip)
+        i += 2
+    return skip, outs
+
+
 def mapping_ref(p: Dict[str, Tensor], z: Tensor, n_mlp: int = 8, lr_mlp: float = 0.01) -> Tensor:
     """models/stylegan2/model.py:16-21 PixelNorm + :383-393 eight EqualLinear
     (lr_mul=0.01, fused_lrelu)."""

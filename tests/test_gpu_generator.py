@@ -132,3 +132,35 @@ def test_generator1024_golden_and_batch_properties(M, golden_dir):
     assert float((img4[0] - img[0]).abs().max()) < 1e-4
     one, _ = gen([lat4[3:4]], input_is_latent=True, noise=noise)
     assert float((img4[3] - one[0]).abs().max()) < 1e-4
+
+
+def test_fse_generator_variant_golden(M, golden_dir):
+    """the FeatureStyleEncoder generator copy (features_in at idx 5, feature_scale=1,
+    return_features=True) -- the call Trainer.get_image makes (trainer.py:295)."""
+    import hairfastgan_b200.fse_model as FM
+    g = np.load(os.path.join(golden_dir, "generator256_fse.npz"))
+    gen = FM.Generator(256, 512, 8)
+    gen.load_state_dict(O.synth_generator_params(size=256, seed=0), strict=True)
+    gen = gen.cuda().eval()
+    lat = torch.from_numpy(np.load(os.path.join(golden_dir, "generator256.npz"))["latent"]).cuda()
+    noise = _cuda_list(O.synth_noise(256, batch=2, seed=3))
+    fea = torch.randn(2, 512, 16, 16, generator=torch.Generator().manual_seed(6)).cuda()
+    img, outs = gen([lat], input_is_latent=True, noise=noise, return_features=True,
+                    features_in=[None] * 5 + [fea] + [None] * 12, feature_scale=1.0)
+    assert len(outs) == int(g["n_outs"])
+    tol, tol1 = TOL_RGB[dtype_name()], TOL_SINGLE[dtype_name()] * 3
+    e, rms = rel_err(img[:, :, ::4, ::4], torch.from_numpy(g["image"]))
+    record("gen256_fse_variant", rel_max_err=e, ref_rms=rms)
+    assert e < tol, e
+    assert float((outs[0][:, ::64].cpu() - torch.from_numpy(g["out0"])).abs().max()) < 1e-6
+    for key, sl in [("out4", (slice(None), slice(None, None, 16))), ("out5", (slice(None), slice(None, None, 16))),
+                    ("out6", (slice(None), slice(None, None, 16), slice(None, None, 2), slice(None, None, 2))),
+                    ("out_last", (slice(None), slice(None, None, 16), slice(None, None, 8), slice(None, None, 8)))]:
+        idx = {"out4": 4, "out5": 5, "out6": 6, "out_last": -1}[key]
+        e, _ = rel_err(outs[idx][sl], torch.from_numpy(g[key]))
+        assert e < tol1, (key, e)
+    # plain call without features must equal the main Generator
+    img2, none = gen([lat], input_is_latent=True, noise=noise)
+    assert none is None
+    with pytest.raises(RuntimeError, match="feature_scale == 1.0"):
+        gen([lat], input_is_latent=True, noise=noise, features_in=[None] * 5 + [fea] + [None] * 12, feature_scale=0.5)

@@ -136,3 +136,20 @@ def test_generator1024_full(golden_dir):
     assert (img[:, :, ::16, ::16] - torch.from_numpy(g["image_sub"])).abs().max() < 2e-4
     assert (img[:, :, 511:513] - torch.from_numpy(g["image_rows"])).abs().max() < 2e-4
     assert abs(float(img.double().sum()) - float(g["image_sum"])) < 1e-2 * 3 * 1024
+
+
+def test_generator256_fse_variant(golden_dir):
+    """FeatureStyleEncoder generator copy: insert_feature at latent idx 5 (alpha=1) + return_features."""
+    g = _load(golden_dir, "generator256_fse.npz")
+    p = O.synth_generator_params(size=256, seed=0)
+    lat = torch.from_numpy(_load(golden_dir, "generator256.npz")["latent"])
+    noise = O.synth_noise(256, batch=2, seed=3)
+    fea = torch.randn(2, 512, 16, 16, generator=torch.Generator().manual_seed(6))
+    img, outs = O.generator_fse_ref(p, lat, noise, [None] * 5 + [fea] + [None] * 12, 1.0)
+    assert len(outs) == int(g["n_outs"]) == 14
+    assert (img[:, :, ::4, ::4] - torch.from_numpy(g["image"])).abs().max() < 1e-4
+    assert (outs[0][:, ::64] - torch.from_numpy(g["out0"])).abs().max() < 1e-6
+    assert (outs[4][:, ::16] - torch.from_numpy(g["out4"])).abs().max() < 1e-4
+    assert (outs[5][:, ::16] - torch.from_numpy(g["out5"])).abs().max() < 1e-4
+    assert (outs[6][:, ::16, ::2, ::2] - torch.from_numpy(g["out6"])).abs().max() < 1e-4
+    assert (outs[-1][:, ::16, ::8, ::8] - torch.from_numpy(g["out_last"])).abs().max() < 1e-4
