@@ -32,6 +32,18 @@ class hf_conv_io(C.Structure):
                 ("act_bias", C.c_void_p), ("act", C.c_int), ("y", C.c_void_p), ("workspace", C.c_void_p)]
 
 
+class hf_conv2d_desc(C.Structure):
+    _fields_ = [("cin", C.c_int), ("cout", C.c_int), ("cin_pad", C.c_int), ("ksize", C.c_int), ("stride", C.c_int),
+                ("groups", C.c_int), ("dtype", C.c_int)]
+
+
+class hf_conv2d_io(C.Structure):
+    _fields_ = [("batch", C.c_int), ("height", C.c_int), ("width", C.c_int), ("x16", C.c_void_p),
+                ("shift", C.c_void_p), ("act", C.c_int), ("slope", C.c_void_p), ("slope0", C.c_float),
+                ("residual16", C.c_void_p), ("y16", C.c_void_p), ("y16b_scale", C.c_void_p),
+                ("y16b_shift", C.c_void_p), ("y16b", C.c_void_p), ("y32_nchw", C.c_void_p)]
+
+
 class hf_gen_config(C.Structure):
     _fields_ = [("size", C.c_int), ("style_dim", C.c_int), ("channel_multiplier", C.c_int), ("dtype", C.c_int)]
 
@@ -81,6 +93,19 @@ SYMBOLS = {
     "hf_torgb_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p, C.c_void_p]),
+    "hf_conv2d_packed_bytes": (C.c_size_t, [C.POINTER(hf_conv2d_desc)]),
+    "hf_conv2d_pack": (C.c_int, [C.POINTER(hf_conv2d_desc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hf_conv2d_forward": (C.c_int, [C.POINTER(hf_conv2d_desc), C.c_void_p, C.POINTER(hf_conv2d_io), C.c_void_p]),
+    "hf_nchw_to_nhwc16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_void_p]),
+    "hf_nhwc16_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hf_channel_mean_nhwc16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hf_scale_add_nhwc16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hf_upsample_add_nhwc16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hf_adaptive_avgpool_nhwc16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_void_p]),
     "hf_generator_packed_bytes": (C.c_size_t, [C.POINTER(hf_gen_config)]),
     "hf_generator_workspace_bytes": (C.c_size_t, [C.POINTER(hf_gen_config), C.c_int]),
     "hf_generator_pack": (C.c_int, [C.POINTER(hf_gen_config), C.POINTER(hf_gen_weights), C.c_void_p, C.c_void_p]),

@@ -52,7 +52,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tmap(CUtensorMap* map, int dtype, int rank, void* gaddr, const uint64_t* dims,
-                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes,
+                const uint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -60,7 +61,7 @@ int encode_tmap(CUtensorMap* map, int dtype, int rank, void* gaddr, const uint64
   }
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bx[5], es[5];
-  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
@@ -105,6 +106,7 @@ static int ensure_device() {
   }
   return HF_OK;
 }
+int ensure_device_current() { return ensure_device(); }
 
 }  // namespace hf
 

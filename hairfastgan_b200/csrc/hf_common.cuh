@@ -16,7 +16,8 @@ void set_error(const char* fmt, ...);
 int num_sms();
 // Encode a tiled tensor map; returns HF_OK or an error (message in hf_last_error()).
 int encode_tmap(CUtensorMap* map, int dtype, int rank, void* gaddr, const uint64_t* dims,
-                const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, int swizzle_bytes);
+                const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, int swizzle_bytes,
+                const uint32_t* elem_strides = nullptr);
 
 #define HF_REQUIRE(cond, ...)                                  \
   do {                                                         \

@@ -64,6 +64,17 @@ struct ConvKernelParams {
   const float* rgb_w;
   const float* rgb_s;
   float* rgb_partial;
+  // plain (encoder) convolution: epi == 1 -> v = act(acc*scale[o] + shift[o]) + residual;
+  // y16 (= xhat_out) = v ; y16b = v*s2[o] + b2[o] ; out_nchw = v
+  int epi, stride, cin_g, cout_g, enc_act;
+  float enc_slope0;
+  const float* enc_scale;
+  const float* enc_shift;
+  const float* enc_slope;
+  const float* enc_s2;
+  const float* enc_b2;
+  const uint16_t* enc_residual;
+  uint16_t* enc_y16b;
 };
 
 struct __align__(16) TableEntry {
@@ -86,13 +97,20 @@ __device__ __forceinline__ MTile decode_mtile(const ConvKernelParams& p, int mt)
 // (the four parity column groups of an up-conv share an entry).  Called by the 128 threads of one group.
 __device__ __forceinline__ void fill_table(const ConvKernelParams& p, TableEntry* table, int etid, int bt, int n0) {
   const int nc_tile = p.up ? p.n_tile / 4 : p.n_tile;
-  for (int e = etid; e < p.TB * nc_tile; e += 128) {
+  const int rows = p.epi == 1 ? 1 : p.TB;      // the encoder table is per channel only
+  for (int e = etid; e < rows * nc_tile; e += 128) {
     const int ebb = e / nc_tile, ol = e - ebb * nc_tile;
     const int eb = bt * p.TB + ebb;
     const int o = (p.up ? (n0 >> 2) : n0) + ol;
     TableEntry t;
     t.d = 1.f; t.bias = 0.f; t.s_next = 1.f; t.pad = 0.f; t.w0 = t.w1 = t.w2 = 0.f; t.pad2 = 0.f;
-    if (eb < p.B) {
+    if (p.epi == 1) {            // encoder: {scale, shift, slope, -, s2, b2}
+      if (p.enc_scale) t.d = __ldg(p.enc_scale + o);
+      if (p.enc_shift) t.bias = __ldg(p.enc_shift + o);
+      t.s_next = p.enc_slope ? __ldg(p.enc_slope + o) : p.enc_slope0;
+      t.w0 = p.enc_s2 ? __ldg(p.enc_s2 + o) : 1.f;
+      t.w1 = p.enc_b2 ? __ldg(p.enc_b2 + o) : 0.f;
+    } else if (eb < p.B) {
       const size_t bo = (size_t)eb * p.Cout + o;
       if (p.d) t.d = __ldg(p.d + bo);
       if (p.bias) t.bias = __ldg(p.bias + o);
@@ -125,6 +143,71 @@ __device__ __forceinline__ float4 load_noise(const ConvKernelParams& p, int b, i
   return nz;
 }
 
+// Encoder epilogue (plain conv + folded BatchNorm / bias + PReLU | LeakyReLU | ReLU + residual):
+//   v = act(acc*scale[o] + shift[o]) + residual ; y16 = v ; y16b = v*s2[o] + b2[o] ; y32 (NCHW) = v
+// (reference: bottleneck_IR_SE / IBasicBlock conv stacks, encoder4editing/models/encoders/helpers.py:98-120,
+//  FeatureStyleEncoder/arcface/iresnet.py:28-57; GradualStyleBlock psp_encoders.py:34-55)
+template <int DT, bool REMOTE_RELEASE>
+__device__ __forceinline__ void epilogue_tile_enc(const ConvKernelParams& p, const TableEntry* trow, uint32_t taddr,
+                                                  uint64_t* release_bar, int n0, int b, int y, int x, bool valid) {
+  const int chunks = p.n_tile / 32;
+  const size_t plane_o = (size_t)p.Ho * p.Wo;
+  const size_t pix = valid ? ((size_t)b * p.Ho + y) * p.Wo + x : 0;
+  for (int q = 0; q < chunks; ++q) {
+    uint32_t acc[32];
+    tmem_ld_32x32(taddr + q * 32, acc);
+    tmem_ld_wait();
+    if (release_bar && q == chunks - 1) {
+      tc_fence_before();
+      if (REMOTE_RELEASE) mbar_arrive_leader(release_bar); else mbar_arrive(release_bar);
+    }
+    const int o_base = n0 + q * 32;
+    uint32_t res[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) res[i] = 0u;
+    if (p.enc_residual && valid) {
+      const uint4* rp = reinterpret_cast<const uint4*>(p.enc_residual + pix * p.Cout + o_base);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 r = __ldg(rp + i);
+        res[4 * i] = r.x; res[4 * i + 1] = r.y; res[4 * i + 2] = r.z; res[4 * i + 3] = r.w;
+      }
+    }
+    float* onchw = (p.out_nchw && valid) ? p.out_nchw + ((size_t)b * p.Cout + o_base) * plane_o + (size_t)y * p.Wo + x
+                                         : nullptr;
+    uint32_t packed[16], packed_b[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      float v[2], vb[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const TableEntry& t = trow[q * 32 + j + u];
+        float a = fmaf(__uint_as_float(acc[j + u]), t.d, t.bias);
+        if (p.enc_act == 1 || p.enc_act == 2) a = a > 0.f ? a : a * t.s_next;
+        else if (p.enc_act == 3) a = fmaxf(a, 0.f);
+        a += Half2T<DT>::to_float((uint16_t)(u ? (res[j >> 1] >> 16) : (res[j >> 1] & 0xFFFFu)));
+        if (onchw) onchw[(size_t)(j + u) * plane_o] = a;
+        v[u] = a;
+        vb[u] = fmaf(a, t.w0, t.w1);
+      }
+      packed[j >> 1] = Half2T<DT>::pack(v[0], v[1]);
+      packed_b[j >> 1] = Half2T<DT>::pack(vb[0], vb[1]);
+    }
+    if (p.xhat_out && valid) {
+      uint4* dst = reinterpret_cast<uint4*>(p.xhat_out + pix * p.Cout + o_base);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+    }
+    if (p.enc_y16b && valid) {
+      uint4* dst = reinterpret_cast<uint4*>(p.enc_y16b + pix * p.Cout + o_base);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        dst[i] = make_uint4(packed_b[4 * i], packed_b[4 * i + 1], packed_b[4 * i + 2], packed_b[4 * i + 3]);
+    }
+  }
+}
+
 // TMEM -> registers -> fused epilogue -> global, for one tile and one thread (= one GEMM row = one pixel).
 //   a = acc*d + nw*noise + bias ; a = lrelu(a)*sqrt2 ; rgb += a*wrgb ; out16 = a*s_next
 // `release_bar` != nullptr: arrive on it right after the last TMEM read (hands the accumulator back).
@@ -132,6 +215,10 @@ template <int DT, bool REMOTE_RELEASE = false>
 __device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, const TableEntry* trow, uint32_t taddr,
                                               uint64_t* release_bar, int n0, int nt, int b, int y, int x, bool valid,
                                               float4 nz) {
+  if (p.epi == 1) {
+    epilogue_tile_enc<DT, REMOTE_RELEASE>(p, trow, taddr, release_bar, n0, b, y, x, valid);
+    return;
+  }
   const int chunks = p.n_tile / 32;
   const size_t plane_o = (size_t)p.Ho * p.Wo;
   float rgb[4][3];
@@ -253,6 +340,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int nt = tile % p.num_n_tiles;
         const MTile tc = decode_mtile(p, tile / p.num_n_tiles);
         const int b0 = tc.bt * p.TB, n0 = nt * p.n_tile;
+        const int c_off = (n0 / p.cout_g) * p.cin_g;        // grouped weights: this N tile's input channels
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dy = (p.taps == 9) ? tap / 3 : 0, dx = (p.taps == 9) ? tap % 3 : 0;
           for (int kc = 0; kc < p.kc_per_tap; ++kc) {
@@ -260,8 +348,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint8_t* a_dst = stage_base + (size_t)stage * p.stage_bytes;
             uint8_t* b_dst = a_dst + p.a_bytes;
             mbar_expect_tx(&full_bar[stage], tx_bytes);
-            tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * KCHUNK, tc.x0 + dx - pad, tc.y0 + dy - pad, b0);
-            tma_load_2d(b_dst, &tmB, &full_bar[stage], tap * p.Cin + kc * KCHUNK, n0);
+            // stride 2: the tensor map walks every other input pixel (TMA element strides)
+            tma_load_4d(a_dst, &tmA, &full_bar[stage], c_off + kc * KCHUNK, tc.x0 * p.stride + dx - pad,
+                        tc.y0 * p.stride + dy - pad, b0);
+            tma_load_2d(b_dst, &tmB, &full_bar[stage], tap * p.cin_g + kc * KCHUNK, n0);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -326,7 +416,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * 256);
-      epilogue_tile<DT>(p, table + bb * nc_tile, taddr, &tmem_empty[buf], n0, nt, b, y, x, valid, nz);
+      epilogue_tile<DT>(p, table + (p.epi == 1 ? 0 : bb * nc_tile), taddr, &tmem_empty[buf], n0, nt, b, y, x, valid, nz);
     }
   }
 
@@ -411,25 +501,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (p.b_resident) {                    // whole weight matrix of this layer: loaded once, never released
         mbar_expect_tx(&b_full[0], 9 * tap_bytes);
         for (int tap = 0; tap < 9; ++tap)
-          tma_load_2d(b_base + (size_t)tap * tap_bytes, &tmB, &b_full[0], tap * p.Cin, 0);
+          tma_load_2d(b_base + (size_t)tap * tap_bytes, &tmB, &b_full[0], tap * p.cin_g, 0);
       }
       for (int w = blockIdx.x; w < p.num_tiles; w += gridDim.x) {
         const int nt = w % p.num_n_tiles, m0 = (w / p.num_n_tiles) * G;
         const int gcount = min(G, p.num_m_tiles - m0);
         const int n0 = nt * p.n_tile;
+        const int c_off = (n0 / p.cout_g) * p.cin_g;
         for (int kc = 0; kc < p.kc_per_tap; ++kc) {
           for (int g = 0; g < gcount; ++g) {
             const MTile tc = decode_mtile(p, m0 + g);
             mbar_wait(&a_empty[as], aphase ^ 1);
             mbar_expect_tx(&a_full[as], a_tx);
-            tma_load_4d(a_base + (size_t)as * a_slot, &tmA, &a_full[as], kc * KCHUNK, tc.x0 - 1, tc.y0 - 1, tc.bt);
+            tma_load_4d(a_base + (size_t)as * a_slot, &tmA, &a_full[as], c_off + kc * KCHUNK, tc.x0 - 1, tc.y0 - 1, tc.bt);
             if (++as == NA) { as = 0; aphase ^= 1; }
           }
           if (!p.b_resident) {
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(&b_empty[bs], bphase ^ 1);
               mbar_expect_tx(&b_full[bs], tap_bytes);
-              tma_load_2d(b_base + (size_t)bs * tap_bytes, &tmB, &b_full[bs], tap * p.Cin + kc * KCHUNK, n0);
+              tma_load_2d(b_base + (size_t)bs * tap_bytes, &tmB, &b_full[bs], tap * p.cin_g + kc * KCHUNK, n0);
               if (++bs == p.stages) { bs = 0; bphase ^= 1; }
             }
           }
@@ -650,15 +741,16 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int nt = w % p.num_n_tiles;
         const MTile tc = decode_mtile(p, 2 * (w / p.num_n_tiles) + (int)rank);
         const int n0 = nt * 256 + (int)rank * 128;
+        const int c_off = ((nt * 256) / p.cout_g) * p.cin_g;
         for (int kc = 0; kc < p.kc_per_tap; ++kc) {
           mbar_wait(&a_empty[as], aphase ^ 1);
           if (leader) mbar_expect_tx(&a_full[as], 2 * A_TX); else mbar_arrive_leader(&a_full[as]);
-          tma2_load_4d(a_base + (size_t)as * a_slot, &tmA, &a_full[as], kc * KCHUNK, tc.x0 - 1, tc.y0 - 1, tc.bt);
+          tma2_load_4d(a_base + (size_t)as * a_slot, &tmA, &a_full[as], c_off + kc * KCHUNK, tc.x0 - 1, tc.y0 - 1, tc.bt);
           if (++as == NA) { as = 0; aphase ^= 1; }
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_empty[bs], bphase ^ 1);
             if (leader) mbar_expect_tx(&b_full[bs], 2 * B_HALF); else mbar_arrive_leader(&b_full[bs]);
-            tma2_load_2d(b_base + (size_t)bs * B_HALF, &tmB, &b_full[bs], tap * p.Cin + kc * KCHUNK, n0);
+            tma2_load_2d(b_base + (size_t)bs * B_HALF, &tmB, &b_full[bs], tap * p.cin_g + kc * KCHUNK, n0);
             if (++bs == NS) { bs = 0; bphase ^= 1; }
           }
         }
@@ -753,42 +845,52 @@ static int env_int(const char* name, int dflt) {
 int conv_plan(const ConvLaunch& a, ConvPlan* p) {
   HF_REQUIRE(a.B > 0 && a.H > 0 && a.W > 0, "conv: bad shape B=%d H=%d W=%d", a.B, a.H, a.W);
   HF_REQUIRE(a.taps == 9 || a.taps == 1, "conv: taps must be 9 or 1");
-  HF_REQUIRE(a.Cin % 32 == 0 && a.Cin >= 32, "conv: Cin=%d must be a multiple of 32", a.Cin);
+  const int stride = a.stride ? a.stride : 1, groups = a.groups ? a.groups : 1;
+  HF_REQUIRE(stride == 1 || stride == 2, "conv: stride %d unsupported", stride);
+  HF_REQUIRE(groups >= 1 && a.Cin % groups == 0 && a.Cout % groups == 0, "conv: bad group count %d", groups);
+  HF_REQUIRE(!(a.up && (stride != 1 || groups != 1)), "conv: upsample excludes stride / groups");
+  const int cin_g = a.Cin / groups;
+  HF_REQUIRE(cin_g % 32 == 0 && cin_g >= 32, "conv: Cin per group = %d must be a multiple of 32", cin_g);
   HF_REQUIRE(a.Cout % 32 == 0 && a.Cout >= 32, "conv: Cout=%d must be a multiple of 32", a.Cout);
   HF_REQUIRE(!a.up || a.taps == 9, "conv: upsample needs a 3x3 kernel");
-  p->halo = (a.taps == 9 && a.H % kHaloTH == 0 && a.W % kHaloTW == 0 && !env_int("HF_CONV_V1", 0)) ? 1 : 0;
+  HF_REQUIRE(stride == 1 || (a.H % 2 == 0 && a.W % 2 == 0) || (a.H == 1 && a.W == 1), "conv: stride 2 needs even H, W");
+  // the GEMM rows are OUTPUT pixels (input pixels for the polyphase up-conv)
+  const int MH = stride == 2 ? (a.H + 1) / 2 : a.H, MW = stride == 2 ? (a.W + 1) / 2 : a.W;
+  p->halo = (a.taps == 9 && stride == 1 && a.H % kHaloTH == 0 && a.W % kHaloTW == 0 && !env_int("HF_CONV_V1", 0)) ? 1 : 0;
   p->G = 1; p->na_slots = 0; p->pitch = 0; p->b_resident = 0; p->a_slot_bytes = 0;
   if (p->halo) {
     p->TW = kHaloTW; p->TH = kHaloTH; p->TB = 1;
   } else {
-    p->TW = a.W < 16 ? a.W : 16;
-    HF_REQUIRE(128 % p->TW == 0, "conv: width %d unsupported (tile width must divide 128)", a.W);
-    p->TH = a.H < 128 / p->TW ? a.H : 128 / p->TW;
-    HF_REQUIRE(128 % (p->TW * p->TH) == 0, "conv: %dx%d image does not tile into 128 GEMM rows", a.H, a.W);
+    p->TW = MW < 16 ? MW : 16;
+    HF_REQUIRE(128 % p->TW == 0, "conv: width %d unsupported (tile width must divide 128)", MW);
+    p->TH = MH < 128 / p->TW ? MH : 128 / p->TW;
+    HF_REQUIRE(128 % (p->TW * p->TH) == 0, "conv: %dx%d image does not tile into 128 GEMM rows", MH, MW);
     p->TB = 128 / (p->TW * p->TH);
   }
-  HF_REQUIRE(a.W % p->TW == 0 && a.H % p->TH == 0, "conv: %dx%d not divisible by tile %dx%d", a.H, a.W, p->TH, p->TW);
-  p->tiles_x = a.W / p->TW;
-  p->tiles_y = a.H / p->TH;
+  HF_REQUIRE(MW % p->TW == 0 && MH % p->TH == 0, "conv: %dx%d not divisible by tile %dx%d", MH, MW, p->TH, p->TW);
+  p->tiles_x = MW / p->TW;
+  p->tiles_y = MH / p->TH;
   p->tiles_b = (a.B + p->TB - 1) / p->TB;
   p->num_m_tiles = p->tiles_x * p->tiles_y * p->tiles_b;
-  p->kchunk = (a.Cin % 64 == 0) ? 64 : 32;
+  p->kchunk = (cin_g % 64 == 0) ? 64 : 32;
   const int ntot = a.up ? 4 * a.Cout : a.Cout;
+  const int cout_g = ntot / groups;                  // an N tile never straddles two groups
   const int nmin = a.up ? 128 : 32;
   const int sms = num_sms();
   const int table_cap = p->halo ? 256 : 512;       // entries per epilogue group
+  const int tb_rows = a.epi == 1 ? 1 : p->TB;      // encoder epilogue tables are per channel only
   int n_tile = 0;
   if (a.force_n_tile) {
     n_tile = a.force_n_tile;
   } else {
     for (int cand = 256; cand >= nmin; cand >>= 1) {
-      if (ntot % cand || p->TB * (a.up ? cand / 4 : cand) > table_cap) continue;
+      if (cout_g % cand || tb_rows * (a.up ? cand / 4 : cand) > table_cap) continue;
       n_tile = cand;
       if ((int64_t)p->num_m_tiles * (ntot / cand) >= sms) break;   // largest tile that still fills the GPU
     }
   }
-  HF_REQUIRE(n_tile >= nmin && n_tile <= 256 && ntot % n_tile == 0 && n_tile % 32 == 0 &&
-                 p->TB * (a.up ? n_tile / 4 : n_tile) <= table_cap,
+  HF_REQUIRE(n_tile >= nmin && n_tile <= 256 && cout_g % n_tile == 0 && n_tile % 32 == 0 &&
+                 tb_rows * (a.up ? n_tile / 4 : n_tile) <= table_cap,
              "conv: no valid N tile (Ntot=%d, n_tile=%d, TB=%d)", ntot, n_tile, p->TB);
   p->n_tile = n_tile;
   p->num_n_tiles = ntot / n_tile;
@@ -807,7 +909,7 @@ int conv_plan(const ConvLaunch& a, ConvPlan* p) {
     p->pitch = kHaloPitch;
     p->a_slot_bytes = (uint32_t)(((size_t)kHaloRows * p->pitch * row_bytes + 1023) & ~size_t(1023));
     const size_t tap_bytes = (size_t)n_tile * row_bytes;
-    const int kc = a.Cin / p->kchunk;
+    const int kc = cin_g / p->kchunk;
     p->b_resident = (kc == 1 && p->num_n_tiles == 1 && 9 * tap_bytes + 2 * (size_t)p->a_slot_bytes <= budget &&
                      env_int("HF_HALO_RESIDENT", 1))
                         ? 1 : 0;
@@ -907,17 +1009,23 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st, ConvPlan* plan_out) {
   HF_REQUIRE((((uintptr_t)a.xhat_in | (uintptr_t)a.wpk | (uintptr_t)a.xhat_out) & 15) == 0,
              "conv: 16-bit tensors must be 16-byte aligned");
 
+  const int stride = a.stride ? a.stride : 1, groups = a.groups ? a.groups : 1;
+  const int cin_g = a.Cin / groups;
   alignas(64) CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
     uint64_t strides[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.W * a.Cin * 2, (uint64_t)a.H * a.W * a.Cin * 2};
     uint32_t box[4] = {(uint32_t)pl.kchunk, (uint32_t)pl.TW, (uint32_t)pl.TH, (uint32_t)pl.TB};
+    uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
     if (pl.halo) { box[1] = (uint32_t)pl.pitch; box[2] = kHaloRows; box[3] = 1; }
-    rc = encode_tmap(&tmA, a.dtype, 4, const_cast<void*>(a.xhat_in), dims, strides, box, pl.kchunk * 2);
+    // stride 2: the box is traversed with element stride 2, so it must span 2*T elements to deliver T samples
+    if (stride == 2) { box[1] = (uint32_t)pl.TW * 2; box[2] = (uint32_t)pl.TH * 2; }
+    rc = encode_tmap(&tmA, a.dtype, 4, const_cast<void*>(a.xhat_in), dims, strides, box, pl.kchunk * 2,
+                     stride == 2 ? es : nullptr);
     if (rc) return rc;
   }
   {
-    const uint64_t K = (uint64_t)a.taps * a.Cin;
+    const uint64_t K = (uint64_t)a.taps * cin_g;
     const uint64_t N = a.up ? 4ull * a.Cout : (uint64_t)a.Cout;
     uint64_t dims[2] = {K, N};
     uint64_t strides[1] = {K * 2};
@@ -928,13 +1036,13 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st, ConvPlan* plan_out) {
 
   ConvKernelParams kp;
   kp.B = a.B; kp.H = a.H; kp.W = a.W; kp.Cin = a.Cin; kp.Cout = a.Cout;
-  kp.Ho = a.up ? 2 * a.H : a.H;
-  kp.Wo = a.up ? 2 * a.W : a.W;
+  kp.Ho = a.up ? 2 * a.H : (stride == 2 ? (a.H + 1) / 2 : a.H);
+  kp.Wo = a.up ? 2 * a.W : (stride == 2 ? (a.W + 1) / 2 : a.W);
   kp.taps = a.taps; kp.up = a.up; kp.act = a.act;
   kp.TW = pl.TW; kp.TH = pl.TH; kp.TB = pl.TB; kp.tiles_x = pl.tiles_x; kp.tiles_y = pl.tiles_y;
   kp.n_tile = pl.n_tile; kp.num_n_tiles = pl.num_n_tiles; kp.num_tiles = pl.num_tiles;
   kp.num_m_tiles = pl.num_m_tiles;
-  kp.kc_per_tap = a.Cin / pl.kchunk;
+  kp.kc_per_tap = cin_g / pl.kchunk;
   kp.num_kb = a.taps * kp.kc_per_tap;
   kp.stages = pl.stages;
   kp.a_bytes = 128u * pl.kchunk * 2;
@@ -953,6 +1061,14 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st, ConvPlan* plan_out) {
   kp.rgb_w = a.rgb_partial ? a.rgb_w : nullptr;
   kp.rgb_s = a.rgb_s;
   kp.rgb_partial = a.rgb_partial;
+  kp.epi = a.epi; kp.stride = stride; kp.cin_g = cin_g;
+  kp.cout_g = (a.up ? 4 * a.Cout : a.Cout) / groups;
+  kp.enc_act = a.enc_act; kp.enc_slope0 = a.enc_slope0;
+  kp.enc_scale = a.enc_scale; kp.enc_shift = a.enc_shift; kp.enc_slope = a.enc_slope;
+  kp.enc_s2 = a.enc_s2; kp.enc_b2 = a.enc_b2;
+  kp.enc_residual = (const uint16_t*)a.enc_residual;
+  kp.enc_y16b = (uint16_t*)a.enc_y16b;
+  HF_REQUIRE(!a.epi || !a.up, "conv: the encoder epilogue has no upsampling form");
   if (plan_out) *plan_out = pl;
 
   const bool bf = a.dtype == HF_BF16;

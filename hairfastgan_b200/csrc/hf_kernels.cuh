@@ -52,6 +52,21 @@ int launch_pack_conv(const float* w, const float* blur, void* wpk, float* wsq, i
                      int up, int nc, int dtype, cudaStream_t st);
 int launch_scale_copy(const float* src, float* dst, int64_t n, float scale, cudaStream_t st);
 
+// ---- hf_enc_ops.cu : encoder-side glue kernels -------------------------------------------------
+int launch_pack_conv2d(const float* w, const float* out_scale, void* wpk, int cout, int cin_g, int cin_pad, int ksize,
+                       int dtype, cudaStream_t st);
+int launch_nchw_to_nhwc16(const float* x, const float* scale, const float* shift, void* y16, int B, int C, int Cpad,
+                          int HW, int dtype, cudaStream_t st);
+int launch_nhwc16_to_nchw(const void* x16, float* y, int B, int C, int HW, int dtype, cudaStream_t st);
+int launch_channel_mean(const void* x16, float* mean, int B, int HW, int C, int dtype, cudaStream_t st);
+int launch_scale_add(const void* res16, const float* se, const void* shortcut16, int sc_stride, const float* s2,
+                     const float* b2, void* y16, void* y16b, int B, int H, int W, int C, int dtype, cudaStream_t st);
+int launch_upsample_add(const void* x16, const void* y16, void* out16, int B, int h, int w, int H, int W, int C,
+                        int dtype, cudaStream_t st);
+int launch_adaptive_avgpool(const void* x16, float* y, int B, int H, int W, int C, int oh, int ow, int dtype,
+                            cudaStream_t st);
+int ensure_device_current();
+
 // ---- hf_conv_tc.cu : tcgen05 implicit-GEMM convolution ----------------------------------------
 struct ConvLaunch {
   int B, H, W;            // input spatial size
@@ -75,6 +90,19 @@ struct ConvLaunch {
   const float* rgb_s;     // [B,Cout] ToRGB modulation
   float* rgb_partial;     // [num_n_tiles][B,3,Ho,Wo]
   int force_n_tile;       // 0 = auto
+  // ---- plain (encoder) convolution: epi = 1 selects the affine / PReLU / residual epilogue
+  int epi;                // 0 generator epilogue, 1 encoder epilogue
+  int stride;             // 1 or 2 (0 = 1)
+  int groups;             // grouped weights: N tile g reads input channels [g*Cin/groups, ...)
+  const float* enc_scale; // [Cout] accumulator scale (NULL = 1)
+  const float* enc_shift; // [Cout] bias / BN shift (NULL = 0)
+  int enc_act;            // 0 none, 1 PReLU(enc_slope[Cout]), 2 LeakyReLU(enc_slope0), 3 ReLU
+  const float* enc_slope;
+  float enc_slope0;
+  const void* enc_residual;   // [B,Ho,Wo,Cout] 16-bit NHWC added after the activation, or NULL
+  const float* enc_s2;    // second 16-bit output: y16b = v*s2[o] + b2[o] (the consumer's pre-conv BatchNorm)
+  const float* enc_b2;
+  void* enc_y16b;
 };
 struct ConvPlan {
   int halo;               // 1: conv_halo_kernel (halo tile in smem, shifted descriptors); 0: conv_igemm_kernel

@@ -1,0 +1,150 @@
+"""Thin Python layer over the encoder entry points of libhairfast_sm100.so (include/hairfast_b200.h,
+"Encoder backbones"): NHWC 16-bit activations, tcgen05 convolutions with folded BatchNorm / PReLU /
+LeakyReLU / residual epilogues, and the HBM-bound glue kernels around them.  CUDA only, forward only."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .model import default_dtype
+
+
+def torch_dtype(dt: Optional[int] = None):
+    dt = default_dtype() if dt is None else dt
+    return torch.float16 if dt == _lib.HF_F16 else torch.bfloat16
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t):
+    return None if t is None else t.detach().float().contiguous()
+
+
+def bn_affine(bn: torch.nn.BatchNorm2d):
+    """Eval-mode BatchNorm2d as y = x * scale + shift."""
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+def to_nhwc16(x: torch.Tensor, scale=None, shift=None, c_pad: Optional[int] = None, dtype: Optional[int] = None):
+    """[B,C,H,W] fp32 NCHW -> [B,H,W,c_pad] 16-bit NHWC (optionally x*scale[c]+shift[c]; zero channel padding)."""
+    if not x.is_cuda:
+        raise RuntimeError("to_nhwc16: input must be a CUDA tensor (no CPU fallback)")
+    dt = default_dtype() if dtype is None else dtype
+    xf = _f32(x)
+    b, c, h, w = xf.shape
+    cp = c if c_pad is None else c_pad
+    y = torch.empty(b, h, w, cp, device=x.device, dtype=torch_dtype(dt))
+    sc, sh = _f32(scale), _f32(shift)
+    _lib.use_device(x.device.index)
+    _lib.check(_lib.lib().hf_nchw_to_nhwc16(xf.data_ptr(), _p(sc), _p(sh), y.data_ptr(), b, c, cp, h, w, dt,
+                                            _lib.stream_ptr()), "hf_nchw_to_nhwc16")
+    return y
+
+
+def to_nchw32(x16: torch.Tensor, dtype: Optional[int] = None):
+    dt = default_dtype() if dtype is None else dtype
+    b, h, w, c = x16.shape
+    y = torch.empty(b, c, h, w, device=x16.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hf_nhwc16_to_nchw(x16.data_ptr(), y.data_ptr(), b, c, h, w, dt, _lib.stream_ptr()),
+               "hf_nhwc16_to_nchw")
+    return y
+
+
+class PackedConv2d:
+    """One nn.Conv2d repacked as a K-major 16-bit GEMM operand (once per weight version)."""
+
+    def __init__(self, weight: torch.Tensor, out_scale=None, stride: int = 1, groups: int = 1,
+                 cin_pad: Optional[int] = None, dtype: Optional[int] = None):
+        dt = default_dtype() if dtype is None else dtype
+        cout, cin_g, k, _ = weight.shape
+        cin = cin_g * groups
+        self.desc = _lib.hf_conv2d_desc(cin, cout, cin if cin_pad is None else cin_pad, k, stride, groups, dt)
+        lib = _lib.lib()
+        nbytes = lib.hf_conv2d_packed_bytes(C.byref(self.desc))
+        if nbytes == 0:
+            _lib.check(-1, "hf_conv2d_packed_bytes")
+        self.blob = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+        w, sc = _f32(weight), _f32(out_scale)
+        _lib.use_device(weight.device.index)
+        _lib.check(lib.hf_conv2d_pack(C.byref(self.desc), w.data_ptr(), _p(sc), self.blob.data_ptr(), _lib.stream_ptr()),
+                   "hf_conv2d_pack")
+        self.cout, self.k, self.stride, self.dtype = cout, k, stride, dt
+
+    def __call__(self, x16: torch.Tensor, shift=None, act: int = 0, slope=None, slope0: float = 0.0, residual16=None,
+                 want_y16: bool = True, y16b_affine=None, want_y32: bool = False):
+        """Returns (y16 | None, y16b | None, y32 | None)."""
+        b, h, w, _ = x16.shape
+        ho, wo = ((h + 1) // 2, (w + 1) // 2) if self.stride == 2 else (h, w)
+        dev = x16.device
+        io = _lib.hf_conv2d_io()
+        io.batch, io.height, io.width, io.x16 = b, h, w, x16.data_ptr()
+        keep = [_f32(shift), _f32(slope)]
+        io.shift, io.act, io.slope, io.slope0 = _p(keep[0]), act, _p(keep[1]), float(slope0)
+        if residual16 is not None:
+            io.residual16 = residual16.data_ptr()
+        y16 = y16b = y32 = None
+        if want_y16:
+            y16 = torch.empty(b, ho, wo, self.cout, device=dev, dtype=torch_dtype(self.dtype))
+            io.y16 = y16.data_ptr()
+        if y16b_affine is not None:
+            s2, b2 = _f32(y16b_affine[0]), _f32(y16b_affine[1])
+            keep += [s2, b2]
+            y16b = torch.empty(b, ho, wo, self.cout, device=dev, dtype=torch_dtype(self.dtype))
+            io.y16b_scale, io.y16b_shift, io.y16b = s2.data_ptr(), b2.data_ptr(), y16b.data_ptr()
+        if want_y32:
+            y32 = torch.empty(b, self.cout, ho, wo, device=dev, dtype=torch.float32)
+            io.y32_nchw = y32.data_ptr()
+        _lib.use_device(dev.index)
+        _lib.check(_lib.lib().hf_conv2d_forward(C.byref(self.desc), self.blob.data_ptr(), C.byref(io), _lib.stream_ptr()),
+                   "hf_conv2d_forward")
+        return y16, y16b, y32
+
+
+def channel_mean(x16: torch.Tensor, dtype: Optional[int] = None):
+    dt = default_dtype() if dtype is None else dtype
+    b, h, w, c = x16.shape
+    m = torch.empty(b, c, device=x16.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hf_channel_mean_nhwc16(x16.data_ptr(), m.data_ptr(), b, h * w, c, dt, _lib.stream_ptr()),
+               "hf_channel_mean_nhwc16")
+    return m
+
+
+def scale_add(res16, se=None, shortcut16=None, shortcut_stride: int = 1, y16b_affine=None, want_y16: bool = True,
+              dtype: Optional[int] = None):
+    dt = default_dtype() if dtype is None else dtype
+    b, h, w, c = res16.shape
+    y = torch.empty_like(res16) if want_y16 else None
+    yb, s2, b2 = None, None, None
+    if y16b_affine is not None:
+        s2, b2 = _f32(y16b_affine[0]), _f32(y16b_affine[1])
+        yb = torch.empty_like(res16)
+    sef = _f32(se)
+    _lib.check(_lib.lib().hf_scale_add_nhwc16(res16.data_ptr(), _p(sef), _p(shortcut16), shortcut_stride, _p(s2), _p(b2),
+                                              _p(y), _p(yb), b, h, w, c, dt, _lib.stream_ptr()), "hf_scale_add_nhwc16")
+    return y, yb
+
+
+def upsample_add(x16, y16, dtype: Optional[int] = None):
+    dt = default_dtype() if dtype is None else dtype
+    b, h, w, c = x16.shape
+    _, hh, ww, _ = y16.shape
+    out = torch.empty_like(y16)
+    _lib.check(_lib.lib().hf_upsample_add_nhwc16(x16.data_ptr(), y16.data_ptr(), out.data_ptr(), b, h, w, hh, ww, c, dt,
+                                                 _lib.stream_ptr()), "hf_upsample_add_nhwc16")
+    return out
+
+
+def adaptive_avgpool(x16, oh: int, ow: int, dtype: Optional[int] = None):
+    dt = default_dtype() if dtype is None else dtype
+    b, h, w, c = x16.shape
+    y = torch.empty(b, c, oh, ow, device=x16.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hf_adaptive_avgpool_nhwc16(x16.data_ptr(), y.data_ptr(), b, h, w, c, oh, ow, dt,
+                                                     _lib.stream_ptr()), "hf_adaptive_avgpool_nhwc16")
+    return y

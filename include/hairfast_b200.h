@@ -188,6 +188,67 @@ typedef struct {
 int hf_generator_forward(const hf_gen_config* cfg, const void* packed, const hf_gen_io* io,
                          void* workspace, int* early_exit /* host */, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Encoder backbones on the same convolution kernels:
+ * e4e Encoder4Editing (models/encoder4editing/models/encoders/psp_encoders.py:124-200, helpers.py:57-140)
+ * and FeatureStyleEncoder fs_encoder_v2 (models/FeatureStyleEncoder/nets/feature_style_encoder.py:12-65,
+ * arcface/iresnet.py:28-163).  Activations travel as NHWC 16-bit tensors between the calls.
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct {
+  int cin, cout;   /* logical channels of the nn.Conv2d */
+  int cin_pad;     /* channels of the stored NHWC input (>= cin, multiple of 32 per group; 3 -> 32 for the stem) */
+  int ksize;       /* 1 or 3 (padding = ksize / 2) */
+  int stride;      /* 1 or 2 */
+  int groups;      /* >= 1; used to run the 18 GradualStyleBlock heads as one grouped conv */
+  int dtype;
+} hf_conv2d_desc;
+
+size_t hf_conv2d_packed_bytes(const hf_conv2d_desc* d);
+
+/* Replaces nn.Conv2d weight handling: weight [cout, cin/groups, k, k] fp32; out_scale [cout] (NULL = 1) is
+ * folded into the weights -- the BatchNorm2d that FOLLOWS the conv in bottleneck_IR_SE / IBasicBlock
+ * (eval mode: gamma / sqrt(running_var + eps)); its shift goes to hf_conv2d_io.shift. */
+int hf_conv2d_pack(const hf_conv2d_desc* d, const float* weight, const float* out_scale, void* packed, void* stream);
+
+typedef struct {
+  int batch, height, width; /* input spatial size */
+  const void* x16;          /* [B,H,W,cin_pad*] 16-bit NHWC (for groups > 1: cin_pad * groups channels) */
+  const float* shift;       /* [cout] conv bias and/or BatchNorm shift, or NULL */
+  int act;                  /* 0 none, 1 PReLU(slope[cout]), 2 LeakyReLU(slope0), 3 ReLU */
+  const float* slope;       /* [cout] for PReLU */
+  float slope0;             /* nn.LeakyReLU() default 0.01 in GradualStyleBlock (psp_encoders.py:42,46) */
+  const void* residual16;   /* [B,Ho,Wo,cout] 16-bit NHWC added after the activation, or NULL */
+  void* y16;                /* [B,Ho,Wo,cout] 16-bit NHWC or NULL */
+  const float* y16b_scale;  /* second output y16b = v * scale[c] + shift[c]: the BatchNorm that PRECEDES the next */
+  const float* y16b_shift;  /*   conv (cannot be folded into its weights because of the zero padding)          */
+  void* y16b;
+  float* y32_nchw;          /* [B,cout,Ho,Wo] fp32 NCHW or NULL */
+} hf_conv2d_io;
+
+/* Replaces nn.Conv2d.forward (+ the folded BatchNorm2d / PReLU / LeakyReLU / residual add around it). */
+int hf_conv2d_forward(const hf_conv2d_desc* d, const void* packed, const hf_conv2d_io* io, void* stream);
+
+/* x [B,C,H,W] fp32 NCHW -> y16 [B,H,W,c_pad] 16-bit NHWC, y = x*scale[c] + shift[c] (NULL = identity), zero padded */
+int hf_nchw_to_nhwc16(const float* x, const float* scale, const float* shift, void* y16, int batch, int channels,
+                      int c_pad, int height, int width, int dtype, void* stream);
+/* x16 [B,H,W,C] 16-bit NHWC -> y [B,C,H,W] fp32 NCHW */
+int hf_nhwc16_to_nchw(const void* x16, float* y, int batch, int channels, int height, int width, int dtype,
+                      void* stream);
+/* SEModule.avg_pool (helpers.py:60): mean over H*W -> [B,C] fp32 */
+int hf_channel_mean_nhwc16(const void* x16, float* mean, int batch, int hw, int channels, int dtype, void* stream);
+/* bottleneck_IR_SE tail (helpers.py:117-120): out = res * se[b,c] + shortcut[b, y*s, x*s, c];
+ * se / shortcut16 / y16 / y16b may be NULL; y16b = out * s2[c] + b2[c] */
+int hf_scale_add_nhwc16(const void* res16, const float* se, const void* shortcut16, int shortcut_stride,
+                        const float* s2, const float* b2, void* y16, void* y16b, int batch, int height, int width,
+                        int channels, int dtype, void* stream);
+/* _upsample_add (helpers.py:123-140): bilinear(align_corners=True) upsample of x16 [B,h,w,C] to HxW, plus y16 */
+int hf_upsample_add_nhwc16(const void* x16, const void* y16, void* out16, int batch, int h, int w, int height,
+                           int width, int channels, int dtype, void* stream);
+/* nn.AdaptiveAvgPool2d((oh,ow)) -> fp32 NCHW [B,C,oh,ow] */
+int hf_adaptive_avgpool_nhwc16(const void* x16, float* y, int batch, int height, int width, int channels, int oh,
+                               int ow, int dtype, void* stream);
+
 /* Number of kernels the last hf_generator_forward / hf_conv_forward of this thread launched. */
 int hf_last_launch_count(void);
 

@@ -1,0 +1,40 @@
+"""CPU: pins the encoder oracle (oracle/encoders_oracle.py) against the golden vectors that
+oracle/gen_golden_encoders.py produced from the unmodified reference classes, and pins the state_dict layout
+of our drop-in encoder modules to the reference's (same keys / shapes, strict load)."""
+import os
+import types
+
+import numpy as np
+import torch
+
+from oracle import encoders_oracle as EO
+
+torch.set_grad_enabled(False)
+
+
+def test_e4e_oracle_and_layout(golden_dir):
+    import hairfastgan_b200.encoders as E
+    g = np.load(os.path.join(golden_dir, "encoders.npz"))
+    enc = E.Encoder4Editing(50, "ir_se", types.SimpleNamespace(stylegan_size=1024)).eval()
+    params = EO.synth_params_like(enc, seed=11)
+    assert len(params) == int(g["e4e_n_keys"])
+    enc.load_state_dict(params, strict=True)
+    x = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(12)) * 2 - 1
+    w, taps = EO.e4e_ref(params, x, return_taps=True)
+    assert w.shape == (2, 18, 512)
+    assert float((w - torch.from_numpy(g["e4e_w"])).abs().max()) < 1e-4
+    assert float((taps[23][:, ::32, ::2, ::2] - torch.from_numpy(g["e4e_c3_sub"])).abs().max()) < 1e-4
+
+
+def test_fse_oracle_and_layout(golden_dir):
+    import hairfastgan_b200.encoders as E
+    g = np.load(os.path.join(golden_dir, "encoders.npz"))
+    enc = E.fs_encoder_v2(n_styles=18, opts=None, stride=(2, 2)).eval()
+    params = EO.synth_params_like(enc, seed=21)
+    assert len(params) == int(g["fse_n_keys"])
+    enc.load_state_dict(params, strict=True)
+    x = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(22)) * 2 - 1
+    lat, content = EO.fse_ref(params, x, content_stride=2)
+    assert lat.shape == (2, 18, 512) and content.shape == (2, 512, 16, 16)
+    assert float((lat - torch.from_numpy(g["fse_latent"])).abs().max()) < 1e-4
+    assert float((content[:, ::16] - torch.from_numpy(g["fse_content_sub"])).abs().max()) < 1e-4

@@ -1,0 +1,104 @@
+"""GPU parity of the encoder rows: the drop-in Encoder4Editing / fs_encoder_v2 modules
+(tcgen05 convs with folded BatchNorm / PReLU / SE / residual epilogues) against the reference-generated
+golden vectors and the CPU oracle, plus the plain-conv building block against torch fp32."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import encoders_oracle as EO
+from tests.gpu_util import dtype_name, record, rel_err
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+# stated tolerance: max-abs error / RMS of the reference output after ~50 chained 16-bit convolutions
+TOL_ENC = {"bf16": 8e-2, "fp16": 1.5e-2}
+TOL_CONV = {"bf16": 4e-2, "fp16": 6e-3}     # one conv incl. 16-bit rounding of its input and output
+
+
+@pytest.fixture(scope="module")
+def N():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import hairfastgan_b200.nn16 as N
+    return N
+
+
+@pytest.mark.parametrize("cin,cout,r,k,stride,groups,cin_pad,act,residual", [
+    (64, 64, 32, 3, 1, 1, None, 1, False), (128, 512, 32, 1, 1, 1, None, 0, False),
+    (128, 256, 64, 3, 2, 1, None, 1, False), (64, 128, 32, 1, 2, 1, None, 0, False),
+    (512, 512, 2, 3, 2, 1, None, 2, False), (3, 64, 64, 3, 1, 1, 32, 1, False),
+    (64, 64, 32, 3, 1, 1, None, 0, True), (256, 256, 16, 3, 2, 4, None, 2, False),
+    (512, 1536, 16, 3, 2, 1, None, 2, False),
+])
+def test_conv2d_building_block(N, cin, cout, r, k, stride, groups, cin_pad, act, residual):
+    g = torch.Generator().manual_seed(cin + cout + r)
+    x = torch.randn(3, cin, r, r, generator=g)
+    w = torch.randn(cout, cin // groups, k, k, generator=g) / (k * (cin // groups) ** 0.5)
+    osc, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.3
+    slope = torch.rand(cout, generator=g) * 0.5
+    ref = F.conv2d(x, w, None, stride, k // 2, 1, groups) * osc.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    ref = {0: ref, 1: torch.where(ref > 0, ref, ref * slope.view(1, -1, 1, 1)), 2: F.leaky_relu(ref, 0.01)}[act]
+    res = torch.randn_like(ref) if residual else None
+    if residual:
+        ref = ref + res
+    pc = N.PackedConv2d(w.cuda(), osc.cuda(), stride=stride, groups=groups, cin_pad=cin_pad)
+    y16, _, y32 = pc(N.to_nhwc16(x.cuda(), c_pad=cin_pad), shift=shift.cuda(), act=act,
+                     slope=slope.cuda() if act == 1 else None, slope0=0.01,
+                     residual16=N.to_nhwc16(res.cuda()) if residual else None, want_y32=True)
+    assert rel_err(y32, ref)[0] < TOL_CONV[dtype_name()]
+    assert rel_err(N.to_nchw32(y16), ref)[0] < TOL_CONV[dtype_name()] * 1.5
+
+
+def test_glue_kernels(N):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 64, 16, 16, generator=g)
+    x16 = N.to_nhwc16(x.cuda())
+    xr = N.to_nchw32(x16).cpu()                      # 16-bit rounded copy = exact input of the glue kernels
+    assert float((N.channel_mean(x16).cpu() - xr.mean((2, 3))).abs().max()) < 1e-5
+    y = torch.randn(2, 64, 32, 32, generator=g)
+    y16 = N.to_nhwc16(y.cuda())
+    up = F.interpolate(xr, size=(32, 32), mode="bilinear", align_corners=True) + N.to_nchw32(y16).cpu()
+    assert float((N.to_nchw32(N.upsample_add(x16, y16)).cpu() - up).abs().max()) < 3e-2
+    pool = N.adaptive_avgpool(x16, 3, 3).cpu()
+    assert float((pool - F.adaptive_avg_pool2d(xr, (3, 3))).abs().max()) < 1e-5
+    se = torch.rand(2, 64, generator=g)
+    big = torch.randn(2, 64, 32, 32, generator=g)
+    b16 = N.to_nhwc16(big.cuda())
+    out, _ = N.scale_add(x16, se.cuda(), b16, 2)
+    ref = xr * se.view(2, 64, 1, 1) + N.to_nchw32(b16).cpu()[:, :, ::2, ::2]
+    assert float((N.to_nchw32(out).cpu() - ref).abs().max()) < 3e-2
+
+
+def test_e4e_encoder_golden(N, golden_dir):
+    import hairfastgan_b200.encoders as E
+    g = np.load(os.path.join(golden_dir, "encoders.npz"))
+    enc = E.Encoder4Editing(50, "ir_se", types.SimpleNamespace(stylegan_size=1024)).eval()
+    enc.load_state_dict(EO.synth_params_like(enc, seed=11), strict=True)
+    enc = enc.cuda()
+    x = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(12)) * 2 - 1
+    w = enc(x.cuda())
+    assert w.shape == (2, 18, 512)
+    e, rms = rel_err(w, torch.from_numpy(g["e4e_w"]))
+    record("e4e_encoder_w", rel_max_err=e, ref_rms=rms)
+    assert e < TOL_ENC[dtype_name()], e
+    assert torch.equal(w, enc(x.cuda()))              # deterministic
+
+
+def test_fse_encoder_golden(N, golden_dir):
+    import hairfastgan_b200.encoders as E
+    g = np.load(os.path.join(golden_dir, "encoders.npz"))
+    enc = E.fs_encoder_v2(n_styles=18, opts=None, stride=(2, 2)).eval()
+    enc.load_state_dict(EO.synth_params_like(enc, seed=21), strict=True)
+    enc = enc.cuda()
+    x = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(22)) * 2 - 1
+    lat, content = enc(x.cuda())
+    assert lat.shape == (2, 18, 512) and content.shape == (2, 512, 16, 16)
+    e1, rms1 = rel_err(lat, torch.from_numpy(g["fse_latent"]))
+    e2, rms2 = rel_err(content[:, ::16], torch.from_numpy(g["fse_content_sub"]))
+    record("fse_encoder", latent_rel_max_err=e1, content_rel_max_err=e2, latent_rms=rms1, content_rms=rms2)
+    assert e1 < TOL_ENC[dtype_name()] and e2 < TOL_ENC[dtype_name()], (e1, e2)
