@@ -3,13 +3,16 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--triples T]
 
-A *step* = the generator hot path of T HairFast.swap() triples: the eight Generator.forward calls one
-triple makes (full x3 [FSE recon], 3->3 x3, 0->3 x3, full x1, 0->3 x2, full x1,
-4->8 x1, 5->8 x1 = 1057.6 GFLOP per triple at 1024^2), with the T triples' calls batched together
-(independent triples, BASELINE config 5).  Encoders and the out-of-scope nets (BiSeNet/SEAN/CLIP) are not
-part of the step.  `value` times the step with everything resident in HBM; `e2e` times the same step
-through the public Generator.forward API with HOST (pinned) latents / layer_in features copied in and the
-T final images copied out inside the timed region.
+A *step* = the SURVEY-8 hot path of T HairFast.swap() triples (SURVEY.md Appendix B census), the T triples'
+calls batched together (independent triples, BASELINE config 5):
+  * the eight Generator.forward calls of a triple (full x3 [FSE recon], 3->3 x3, 0->3 x3, full x1, 0->3 x2,
+    full x1, 4->8 x1, 5->8 x1: 1057.6 GFLOP, 1024^2, randomize_noise=True like the reference),
+  * e4e Encoder4Editing on 3 + 2 images and FeatureStyleEncoder fs_encoder_v2 on 3 images at 256^2
+    (720.5 + 208.7 GFLOP),
+i.e. 1986.8 algorithmic GFLOP per triple.  Not in the step: the PostProcess conv stack ("next") and
+the out-of-scope nets (BiSeNet / SEAN / CLIP / mask nets).  `value` times the step with inputs resident in HBM;
+`e2e` times it through the public Python API with HOST (pinned) inputs copied in and the T final images
+copied out inside the timed region.
 
 One JSON line on stdout (rank 0).  Multi-GPU: one process per GPU under torchrun, weights broadcast from
 rank 0 over NCCL at init, no collective in the step; time = max over ranks.
@@ -23,13 +26,17 @@ import subprocess
 import sys
 import threading
 import time
+import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GFLOP_FULL, GFLOP_0_3, GFLOP_3_3, GFLOP_4_8, GFLOP_5_8 = 148.52, 8.007, 6.043, 140.51, 116.34
-GFLOP_PER_TRIPLE = 3 * GFLOP_FULL + 3 * GFLOP_3_3 + 3 * GFLOP_0_3 + GFLOP_FULL + 2 * GFLOP_0_3 + GFLOP_FULL \
+GFLOP_GEN_PER_TRIPLE = 3 * GFLOP_FULL + 3 * GFLOP_3_3 + 3 * GFLOP_0_3 + GFLOP_FULL + 2 * GFLOP_0_3 + GFLOP_FULL \
     + GFLOP_4_8 + GFLOP_5_8                               # = 1057.6
+GFLOP_E4E_IMG, GFLOP_FSE_IMG = 144.1, 69.6
+GFLOP_ENC_PER_TRIPLE = 5 * GFLOP_E4E_IMG + 3 * GFLOP_FSE_IMG
+GFLOP_PER_TRIPLE = GFLOP_GEN_PER_TRIPLE + GFLOP_ENC_PER_TRIPLE
 ROOFLINE_US_PER_IMG = 142.5                               # SURVEY Appendix A, sum of per-layer maxima
 
 
@@ -64,19 +71,22 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        return len(self.rows)
+
+    def stop(self, first: int = 0):
         if self.proc:
             self.proc.terminate()
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        rows = self.rows[first:] or self.rows
+        sm = sorted(int(float(r[0])) for r in rows if r and r[0].replace(".", "").isdigit())
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             for n, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        smax = int(float(self.rows[0][1])) if self.rows else None
-        busy = [v for v in sm if smax and v > 0.5 * smax] or sm
-        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+        smax = int(float(rows[0][1])) if rows else None
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
                 "samples": len(sm)}
 
 
@@ -89,8 +99,9 @@ def census(T: int):
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from hairfastgan_b200 import _lib
+    from hairfastgan_b200 import _lib, sharding
     import hairfastgan_b200.model as M
+    import hairfastgan_b200.encoders as E
     torch.set_grad_enabled(False)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -99,34 +110,48 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     T = args.triples
 
-    # ---- synthetic generator: seeded random weights of the reference architecture (no checkpoints exist)
+    # ---- synthetic networks: seeded random weights of the reference architectures (no checkpoints exist)
     torch.manual_seed(0)
     gen = M.Generator(1024, 512, 8).to(dev).eval()
     for name, prm in gen.named_parameters():
         if name.endswith("noise.weight") or name.endswith("activate.bias") or name == "to_rgb1.bias" \
                 or (name.startswith("to_rgbs.") and name.endswith(".bias") and name.count(".") == 2):
             prm.data.normal_(0, 0.1)
+    e4e = E.Encoder4Editing(50, "ir_se", types.SimpleNamespace(stylegan_size=1024)).to(dev).eval()
+    fse = E.fs_encoder_v2(n_styles=18, opts=None, stride=(2, 2)).to(dev).eval()
+    for net in (e4e, fse):                            # non-trivial BatchNorm statistics
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_var.uniform_(0.5, 1.5)
+                m.running_mean.normal_(0, 0.1)
+    bcast_bytes = 0
     if world > 1:                                     # weights replicated: one NCCL broadcast at init
-        for t in list(gen.parameters()) + list(gen.buffers()):
-            dist.broadcast(t.data, src=0)
+        for net in (gen, e4e, fse):
+            bcast_bytes += sharding.broadcast_module_(net, src=0)
     calls = census(T)
     g = torch.Generator(device="cpu").manual_seed(100 + rank)
     host_lat = [torch.randn(b, 18, 512, generator=g).pin_memory() for (_, _, b, _) in calls]
     host_lin = [None if r is None else torch.randn(b, 512, r, r, generator=g).pin_memory() for (_, _, b, r) in calls]
+    host_img = [(torch.rand(n * T, 3, 256, 256, generator=g) * 2 - 1).pin_memory() for n in (3, 2, 3)]  # e4e, e4e, FSE
     dev_lat = [t.to(dev) for t in host_lat]
     dev_lin = [None if t is None else t.to(dev) for t in host_lin]
+    dev_img = [t.to(dev) for t in host_img]
     host_out = torch.empty(T, 3, 1024, 1024).pin_memory()
     launches = [0]
 
     def step(e2e: bool):
+        img = [t.to(dev, non_blocking=True) for t in host_img] if e2e else dev_img
+        n0 = lib.hf_total_launch_count()
+        for net, x in ((e4e, img[0]), (e4e, img[1]), (fse, img[2])):   # Embedding.py:71,74 / :51
+            net(x)
         final = None
         for i, (s, e, b, r) in enumerate(calls):
             lat = host_lat[i].to(dev, non_blocking=True) if e2e else dev_lat[i]
             lin = None if r is None else (host_lin[i].to(dev, non_blocking=True) if e2e else dev_lin[i])
             out = gen([lat], input_is_latent=True, start_layer=s, end_layer=e, layer_in=lin)   # random noise, as swap()
-            launches[0] += lib.hf_last_launch_count()
             if i == len(calls) - 1:
                 final = out[0]
+        launches[0] += lib.hf_total_launch_count() - n0
         if e2e:
             host_out.copy_(final, non_blocking=True)
         return final
@@ -142,7 +167,6 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         launches[0] = 0
         total_ms = 0.0
-        wall0 = time.perf_counter()
         for _ in range(steps):
             flush.fill_(1)                                             # L2 flush between timed iterations
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -154,45 +178,55 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        wall = time.perf_counter() - wall0
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), wall, launches[0]
+        return sharding.max_over_ranks(total_ms, dev), launches[0]
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms, wall, n_launch = timed(False, args.steps, args.warmup)
-    ms_e2e, _, _ = timed(True, args.steps, max(3, args.warmup // 2))
-    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step(False)                                   # also gives nvidia-smi time to start sampling
+    torch.cuda.synchronize()
+    first = sampler.mark()
+    ms, n_launch = timed(False, args.steps, args.warmup)
+    ms_e2e, _ = timed(True, args.steps, max(3, args.warmup // 2))
+    clocks = sampler.stop(first) if rank == 0 else None
 
-    # ---- configs[1]: full 1024^2 generator forward, B=4, and the dominant kernel alone (configs[0] shape x4)
-    extra = {}
+    extra = {"nccl_broadcast_bytes_at_init": bcast_bytes}
     if rank == 0 and world == 1:
+        def avg_ms(fn, n=5):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            tot = 0.0
+            for _ in range(n):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record(); e1.synchronize()
+                tot += e0.elapsed_time(e1)
+            return tot / n
+        # configs[1]: full 1024^2 generator forward, B=4
         lat4 = torch.randn(4, 18, 512, device=dev)
-        for _ in range(3):
-            gen([lat4], input_is_latent=True)
-        torch.cuda.synchronize()
-        tot = 0.0
-        for _ in range(5):
-            flush.fill_(1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); gen([lat4], input_is_latent=True); e1.record(); e1.synchronize()
-            tot += e0.elapsed_time(e1)
-        us_img = tot / 5 / 4 * 1e3
+        us_img = avg_ms(lambda: gen([lat4], input_is_latent=True)) / 4 * 1e3
         extra["generator_b4"] = {"img_per_s": round(1e6 / us_img, 1), "us_per_img": round(us_img, 1),
                                  "frac_of_roofline_142.5us": round(ROOFLINE_US_PER_IMG / us_img, 4),
                                  "tflops_algorithmic": round(GFLOP_FULL / us_img * 1e3, 1)}
+        # configs[3]: e4e + FSE inversion, 256^2, batch 32
+        x32 = torch.rand(32, 3, 256, 256, device=dev) * 2 - 1
+        ms_e4e, ms_fse = avg_ms(lambda: e4e(x32)), avg_ms(lambda: fse(x32))
+        extra["encoders_b32"] = {"e4e_img_per_s": round(32e3 / ms_e4e, 1), "fse_img_per_s": round(32e3 / ms_fse, 1),
+                                 "e4e_tflops_algorithmic": round(32 * GFLOP_E4E_IMG / ms_e4e, 1),
+                                 "fse_tflops_algorithmic": round(32 * GFLOP_FSE_IMG / ms_fse, 1)}
         extra["roofline"] = time_dominant_kernel(gen, dev)
     if world > 1:
         dist.destroy_process_group()
-    return ms, ms_e2e, n_launch, clocks, extra, host_lat, host_lin
+    h2d = sum(t.numel() * 4 for t in host_lat) + sum(t.numel() * 4 for t in host_lin if t is not None) \
+        + sum(t.numel() * 4 for t in host_img)
+    return ms, ms_e2e, n_launch, clocks, extra, h2d
 
 
 def time_dominant_kernel(gen, dev):
-    """conv_igemm_kernel on the 512->512 3x3 @64^2 layer (BASELINE configs[0] shape), B=4: the layer class that
-    carries most of the tensor-core time.  Algorithmic FLOPs = 2*512*512*9*64^2 per sample."""
+    """The 512->512 3x3 @64^2 convolution (BASELINE configs[0] shape) at B=4: the layer class that carries most of
+    the tensor-core time.  Algorithmic FLOPs = 2*512*512*9*64^2 per sample."""
     import ctypes as C
     import torch
     from hairfastgan_b200 import _lib
@@ -213,30 +247,46 @@ def time_dominant_kernel(gen, dev):
     ms = C.c_float(0)
     _lib.check(lib.hf_conv_time_kernel(C.byref(desc), blob.data_ptr(), C.byref(io), 20, C.byref(ms),
                                        torch.cuda.current_stream().cuda_stream), "hf_conv_time_kernel")
+    plan = (C.c_int * 12)()
+    lib.hf_conv_plan_query(C.byref(desc), B, 64, 64, plan)
+    kname = {0: "conv_igemm_kernel", 1: "conv_halo_kernel", 2: "conv_halo2_kernel (cta_group::2)"}[plan[0]]
     flops = 2.0 * 512 * 512 * 9 * 64 * 64 * B
     achieved = flops / (ms.value * 1e-3) / 1e12
     pk = peaks()
-    return {"kernel": "conv_halo_kernel<64,bf16> 512->512 3x3 @64^2 B=4 (+fp32 NCHW store)", "bound": "tensor",
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_dominant_kernel_r1.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    return {"kernel": f"{kname}<bf16> 512->512 3x3 @64^2 B=4 (+fp32 NCHW store)", "bound": "tensor",
             "achieved": round(achieved, 1), "peak": pk["tf_burst"], "unit": "TFLOP/s",
             "frac": round(achieved / pk["tf_burst"], 4), "peak_source": pk["src"] + " burst (kernel timed alone)",
-            "launch_ms": round(ms.value, 4), "traffic": None}
+            "launch_ms": round(ms.value, 4), "traffic": traffic}
 
 
 def cpu_oracle_sample(threads=None):
-    """The reference algorithm on host cores (oracle port; the reference itself cannot travel to the GPU box):
-    one full 1024^2 generator forward, B=1 (148.52 of the 1057.6 GFLOP of a triple), scaled to triples/s."""
+    """The reference algorithm on host cores (oracle port; the Python reference cannot travel to the GPU box): one
+    full 1024^2 generator forward + one e4e + one FSE encoder forward, B=1 (362.2 of the 1986.8 GFLOP of a triple),
+    scaled to triples/s."""
     import torch
     from oracle import stylegan2_oracle as O
+    from oracle import encoders_oracle as EO
+    import hairfastgan_b200.encoders as E          # parameter containers only (CPU); the math below is the oracle's
     torch.set_grad_enabled(False)
     if threads:
         torch.set_num_threads(threads)
     p = O.synth_generator_params(size=1024, seed=0)
     lat = torch.randn(1, 18, 512, generator=torch.Generator().manual_seed(0))
     noise = O.synth_noise(1024, batch=1, seed=1)
+    pe = EO.synth_params_like(E.Encoder4Editing(50, "ir_se", types.SimpleNamespace(stylegan_size=1024)), 11)
+    pf = EO.synth_params_like(E.fs_encoder_v2(n_styles=18, opts=None, stride=(2, 2)), 21)
+    x = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(12)) * 2 - 1
     t0 = time.perf_counter()
     O.generator_ref(p, lat, noise)
+    EO.e4e_ref(pe, x)
+    EO.fse_ref(pf, x)
     dt = time.perf_counter() - t0
-    return dt, (GFLOP_FULL / GFLOP_PER_TRIPLE) / dt, torch.get_num_threads()
+    frac = (GFLOP_FULL + GFLOP_E4E_IMG + GFLOP_FSE_IMG) / GFLOP_PER_TRIPLE
+    return dt, frac / dt, torch.get_num_threads()
 
 
 def main():
@@ -251,22 +301,22 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = ("generator hot path of HairFast.swap(): the 8 Generator.forward calls per triple "
-                "(SURVEY App. B, 1057.6 GFLOP/triple, 1024^2, randomize_noise=True), synthetic weights; "
-                "encoders and out-of-scope nets excluded")
+    workload = ("SURVEY-8 hot path of HairFast.swap(): 8 Generator.forward calls (1024^2, randomize_noise=True) + "
+                "e4e on 5 and FSE on 3 images (256^2) per triple = 1986.8 GFLOP/triple (App. B census), synthetic "
+                "weights; PostProcess convs and out-of-scope nets (BiSeNet/SEAN/CLIP) excluded")
+    sample = ("one full 1024^2 generator forward + one e4e + one FSE forward, B=1 = 362.2 of 1986.8 GFLOP per "
+              "triple, scaled")
 
     if args.impl == "reference":
         if rank != 0:
             return
-        # the reference's CPU implementation of the path (oracle port, all host threads), bounded sample
         times = []
         for i in range(args.warmup + args.steps):
             dt, tps, thr = cpu_oracle_sample()
             if i >= args.warmup:
                 times.append(dt)
         dt = sum(times) / len(times)
-        val = (GFLOP_FULL / GFLOP_PER_TRIPLE) / dt
-        sample = "one full 1024^2 generator forward B=1 = 148.52 of 1057.6 GFLOP per triple, scaled"
+        val = ((GFLOP_FULL + GFLOP_E4E_IMG + GFLOP_FSE_IMG) / GFLOP_PER_TRIPLE) / dt
         print(json.dumps({
             "impl": "reference", "metric": "hair_swap_triples_per_sec", "value": val, "unit": "triples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -277,14 +327,13 @@ def main():
             "gpu_launches": 0}))
         return
 
-    ms, ms_e2e, n_launch, clocks, extra, host_lat, host_lin = run_ours(args, rank, world, local_rank)
+    ms, ms_e2e, n_launch, clocks, extra, h2d = run_ours(args, rank, world, local_rank)
     if rank != 0:
         return
     T = args.triples
     step_ms = ms / args.steps
     value = world * T / (step_ms * 1e-3)
     e2e_value = world * T / (ms_e2e / args.steps * 1e-3)
-    h2d = sum(t.numel() * 4 for t in host_lat) + sum(t.numel() * 4 for t in host_lin if t is not None)
     out = {
         "metric": "hair_swap_triples_per_sec", "value": round(value, 3), "unit": "triples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 4), "higher_is_better": True,
@@ -302,8 +351,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         dt, tps, thr = cpu_oracle_sample()
         out["cpu_baseline"] = {"value": round(tps, 5), "unit": "triples/s", "cores": thr, "kind": "port",
-                               "sample": f"oracle generator_ref, one full 1024^2 forward B=1 ({dt:.1f} s), "
-                                         "scaled by 148.52/1057.6 GFLOP"}
+                               "sample": f"oracle generator_ref + e4e_ref + fse_ref, B=1 ({dt:.1f} s): " + sample}
     print(json.dumps(out))
 
 

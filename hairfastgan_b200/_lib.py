@@ -80,6 +80,7 @@ SYMBOLS = {
     "hf_set_device": (C.c_int, [C.c_int]),
     "hf_sm_count": (C.c_int, []),
     "hf_last_launch_count": (C.c_int, []),
+    "hf_total_launch_count": (C.c_longlong, []),
     "hf_upfirdn2d_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 13 + [C.c_void_p]),
     "hf_bias_act_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_int,
                                   C.c_float, C.c_float, C.c_void_p]),

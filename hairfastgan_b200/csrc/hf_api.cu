@@ -19,7 +19,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-void count_launch(int n) { g_launches += n; }
+static thread_local long long g_launches_total = 0;
+void count_launch(int n) { g_launches += n; g_launches_total += n; }
+long long total_launch_count() { return g_launches_total; }
 void reset_launch_count() { g_launches = 0; }
 
 int num_sms() {
@@ -117,6 +119,7 @@ extern "C" {
 int hf_version(void) { return 100; }
 const char* hf_last_error(void) { return g_err; }
 int hf_last_launch_count(void) { return g_launches; }
+long long hf_total_launch_count(void) { return hf::total_launch_count(); }
 
 int hf_set_device(int device) {
   int n = 0;

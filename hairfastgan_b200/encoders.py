@@ -242,6 +242,17 @@ class Encoder4Editing(nn.Module):
         return w
 
 
+class GradualStyleEncoder(nn.Module):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("GradualStyleEncoder (pSp) is not on the HairFast path (e4e checkpoints use "
+                                  "encoder_type='Encoder4Editing', utils/model_utils.py:17-28)")
+
+
+class BackboneEncoderUsingLastLayerIntoW(nn.Module):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("BackboneEncoderUsingLastLayerIntoW is not on the HairFast path")
+
+
 # ------------------------------------------------------------------------------------------------
 # FeatureStyleEncoder
 # ------------------------------------------------------------------------------------------------

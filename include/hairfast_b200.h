@@ -251,6 +251,8 @@ int hf_adaptive_avgpool_nhwc16(const void* x16, float* y, int batch, int height,
 
 /* Number of kernels the last hf_generator_forward / hf_conv_forward of this thread launched. */
 int hf_last_launch_count(void);
+/* Number of kernels every hf_* call of this thread has launched since the library was loaded. */
+long long hf_total_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -110,9 +110,16 @@ def test_install_overlay_redirects_reference_imports():
         import importlib
         assert importlib.import_module("models.stylegan2.op").__name__ == "hairfastgan_b200.op"
         assert importlib.import_module("models.stylegan2.model").Generator.__module__ == "hairfastgan_b200.model"
+        fse = importlib.import_module("pixel2style2pixel.models.stylegan2.model")
+        assert fse.Generator.__module__ == "hairfastgan_b200.fse_model" and callable(fse.get_keys)
+        psp = importlib.import_module("models.encoder4editing.models.encoders.psp_encoders")
+        assert psp.Encoder4Editing.__module__ == "hairfastgan_b200.encoders"
+        ns = {}
+        exec("from nets.feature_style_encoder import *", ns)          # trainer.py:20
+        assert ns["fs_encoder_v2"].__module__ == "hairfastgan_b200.encoders"
     finally:
         inst.uninstall()
-    assert "models.stylegan2.op" not in sys.modules
+    assert "models.stylegan2.op" not in sys.modules and "nets" not in sys.modules
 
 
 def test_conv_plans_for_every_generator_layer(lib):
