@@ -180,6 +180,15 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         return sharding.max_over_ranks(total_ms, dev), launches[0]
 
+    if args.profile_step:                             # for `ncu --profile-from-start off`: exactly one step
+        step(False)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step(False)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return None
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -297,6 +306,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--triples", type=int, default=4, help="independent triples batched per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true", help="run one step between cudaProfilerStart/Stop, no JSON")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -327,7 +337,10 @@ def main():
             "gpu_launches": 0}))
         return
 
-    ms, ms_e2e, n_launch, clocks, extra, h2d = run_ours(args, rank, world, local_rank)
+    res = run_ours(args, rank, world, local_rank)
+    if res is None:
+        return
+    ms, ms_e2e, n_launch, clocks, extra, h2d = res
     if rank != 0:
         return
     T = args.triples

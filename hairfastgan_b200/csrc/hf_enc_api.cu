@@ -78,10 +78,26 @@ int hf_nhwc16_to_nchw(const void* x16, float* y, int batch, int channels, int he
   return launch_nhwc16_to_nchw(x16, y, batch, channels, height * width, dtype, (cudaStream_t)stream);
 }
 
-int hf_channel_mean_nhwc16(const void* x16, float* mean, int batch, int hw, int channels, int dtype, void* stream) {
+size_t hf_channel_reduce_workspace_bytes(int batch, int hw, int channels) {
+  if (batch <= 0 || hw <= 0 || channels <= 0) return 0;
+  return (size_t)batch * channel_reduce_splits(batch, hw, channels) * channels * sizeof(float);
+}
+
+int hf_channel_mean_nhwc16(const void* x16, float* mean, void* workspace, int batch, int hw, int channels, int dtype,
+                           void* stream) {
   int rc = ensure_device_current();
   if (rc) return rc;
-  return launch_channel_mean(x16, mean, batch, hw, channels, dtype, (cudaStream_t)stream);
+  return launch_se_gate(x16, nullptr, nullptr, mean, (float*)workspace, batch, hw, channels, 0, dtype,
+                        (cudaStream_t)stream);
+}
+
+int hf_se_gate_nhwc16(const void* x16, const float* fc1_weight, const float* fc2_weight, float* gate, void* workspace,
+                      int batch, int hw, int channels, int reduced, int dtype, void* stream) {
+  int rc = ensure_device_current();
+  if (rc) return rc;
+  HF_REQUIRE(fc1_weight && fc2_weight, "hf_se_gate_nhwc16: null fc weights");
+  return launch_se_gate(x16, fc1_weight, fc2_weight, gate, (float*)workspace, batch, hw, channels, reduced, dtype,
+                        (cudaStream_t)stream);
 }
 
 int hf_scale_add_nhwc16(const void* res16, const float* se, const void* shortcut16, int shortcut_stride,

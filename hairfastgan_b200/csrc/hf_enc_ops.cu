@@ -118,32 +118,97 @@ int launch_nhwc16_to_nchw(const void* x16, float* y, int B, int C, int HW, int d
   return HF_OK;
 }
 
-// mean over HW per (b,c) of an NHWC 16-bit tensor (SEModule.avg_pool, helpers.py:57-75): one CTA per
-// (b, 64-channel slab); fixed summation order -> deterministic
+// Squeeze-excite pooling (SEModule, helpers.py:57-75) in two deterministic stages.
+// Stage 1: per-(b, pixel split, 64-channel slab) partial sums of an NHWC 16-bit tensor.  256 threads = 8 lanes of
+// 8 channels (16-byte loads) x 32 pixel rows; fixed summation order.  part[(b*S + s)*C + c].
 template <int DT>
-__global__ void __launch_bounds__(256) channel_mean_kernel(const uint16_t* __restrict__ x, float* __restrict__ mean,
-                                                           int HW, int C) {
-  __shared__ float part[4][64];
-  const int b = blockIdx.y, c0 = blockIdx.x * 64;
-  const int cl = threadIdx.x & 63, row = threadIdx.x >> 6;      // 4 pixel rows x 64 channels
-  float acc = 0.f;
-  if (c0 + cl < C)
-    for (int p = row; p < HW; p += 4) acc += ld16<DT>(x + ((size_t)b * HW + p) * C + c0 + cl);
-  part[row][cl] = acc;
+__global__ void __launch_bounds__(256) channel_sum_partial_kernel(const uint16_t* __restrict__ x,
+                                                                  float* __restrict__ part, int HW, int C, int chunk) {
+  __shared__ float red[32][65];
+  const int b = blockIdx.y, s = blockIdx.z, S = gridDim.z, c0 = blockIdx.x * 64;
+  const int lane8 = threadIdx.x & 7, row = threadIdx.x >> 3;
+  const int c = c0 + lane8 * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int p0 = s * chunk, p1 = min(HW, p0 + chunk);
+  if (c < C) {
+    for (int p = p0 + row; p < p1; p += 32) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + ((size_t)b * HW + p) * C + c));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[2 * k] += Half2T<DT>::to_float((uint16_t)(w[k] & 0xFFFF));
+        acc[2 * k + 1] += Half2T<DT>::to_float((uint16_t)(w[k] >> 16));
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[row][lane8 * 8 + k] = acc[k];
   __syncthreads();
-  if (row == 0 && c0 + cl < C)
-    mean[(size_t)b * C + c0 + cl] = (part[0][cl] + part[1][cl] + part[2][cl] + part[3][cl]) / (float)HW;
+  if (threadIdx.x < 64 && c0 + threadIdx.x < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t += red[r][threadIdx.x];
+    part[((size_t)b * S + s) * C + c0 + threadIdx.x] = t;
+  }
 }
 
-int launch_channel_mean(const void* x16, float* mean, int B, int HW, int C, int dtype, cudaStream_t st) {
-  HF_REQUIRE(x16 && mean, "channel_mean: null pointer");
-  dim3 grid(cdiv_i(C, 64), B);
+// Stage 2, one CTA per sample: mean[c] = sum_s part / HW; with fc weights, gate = sigmoid(W2 . relu(W1 . mean))
+// (fc1 [Cr,C], fc2 [C,Cr], both bias-free 1x1 convs); without, out = mean.
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ part, int S, float inv_hw,
+                                                      const float* __restrict__ w1, const float* __restrict__ w2,
+                                                      float* __restrict__ out, int C, int Cr) {
+  extern __shared__ float sm[];
+  float* mean = sm;
+  float* hid = sm + C;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int c = tid; c < C; c += 256) {
+    float t = 0.f;
+    for (int s = 0; s < S; ++s) t += part[((size_t)b * S + s) * C + c];
+    mean[c] = t * inv_hw;
+    if (!w1) out[(size_t)b * C + c] = mean[c];
+  }
+  if (!w1) return;
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int j = warp; j < Cr; j += 8) {
+    float t = 0.f;
+    for (int c = lane; c < C; c += 32) t = fmaf(__ldg(w1 + (size_t)j * C + c), mean[c], t);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+    if (lane == 0) hid[j] = fmaxf(t, 0.f);
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += 256) {
+    float t = 0.f;
+    for (int j = 0; j < Cr; ++j) t = fmaf(__ldg(w2 + (size_t)c * Cr + j), hid[j], t);
+    out[(size_t)b * C + c] = 1.f / (1.f + __expf(-t));
+  }
+}
+
+int channel_reduce_splits(int B, int HW, int C) {
+  const int64_t ctas = (int64_t)B * cdiv_i(C, 64);
+  int s = cdiv_i((int64_t)4 * 148, ctas);
+  s = std::min(s, std::max(1, HW / 64));
+  return std::max(1, std::min(s, 64));
+}
+
+// gate/mean [B,C] <- x16 [B,HW,C]; workspace: B * splits * C floats
+int launch_se_gate(const void* x16, const float* fc1, const float* fc2, float* out, float* ws, int B, int HW, int C,
+                   int Cr, int dtype, cudaStream_t st) {
+  HF_REQUIRE(x16 && out && ws, "se_gate: null pointer");
+  HF_REQUIRE(C % 8 == 0 && B > 0 && HW > 0, "se_gate: channels must be a multiple of 8");
+  HF_REQUIRE((fc1 == nullptr) == (fc2 == nullptr) && (!fc1 || (Cr > 0 && Cr <= 4096)), "se_gate: bad fc weights");
+  const int S = channel_reduce_splits(B, HW, C), chunk = cdiv_i(HW, S);
+  dim3 grid(cdiv_i(C, 64), B, S);
   if (dtype == HF_BF16)
-    channel_mean_kernel<HF_BF16><<<grid, 256, 0, st>>>((const uint16_t*)x16, mean, HW, C);
+    channel_sum_partial_kernel<HF_BF16><<<grid, 256, 0, st>>>((const uint16_t*)x16, ws, HW, C, chunk);
   else
-    channel_mean_kernel<HF_F16><<<grid, 256, 0, st>>>((const uint16_t*)x16, mean, HW, C);
-  HF_LAUNCH_OK("channel_mean");
-  count_launch();
+    channel_sum_partial_kernel<HF_F16><<<grid, 256, 0, st>>>((const uint16_t*)x16, ws, HW, C, chunk);
+  HF_LAUNCH_OK("channel_sum_partial");
+  se_gate_kernel<<<B, 256, (size_t)(C + (fc1 ? Cr : 0)) * sizeof(float), st>>>(ws, S, 1.f / (float)HW, fc1, fc2, out, C,
+                                                                                 Cr);
+  HF_LAUNCH_OK("se_gate");
+  count_launch(2);
   return HF_OK;
 }
 
@@ -180,10 +245,84 @@ __global__ void __launch_bounds__(256) scale_add_kernel(const uint16_t* __restri
   }
 }
 
+// same, 8 channels (16 bytes) per thread; C % 8 == 0
+template <int DT>
+__global__ void __launch_bounds__(256) scale_add_vec8_kernel(const uint16_t* __restrict__ res,
+                                                             const float* __restrict__ se,
+                                                             const uint16_t* __restrict__ sc, int sc_stride,
+                                                             const float* __restrict__ s2, const float* __restrict__ b2,
+                                                             uint16_t* __restrict__ y, uint16_t* __restrict__ yb, int H,
+                                                             int W, int C8, int64_t total8) {
+  const int C = C8 * 8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    int64_t t = i / C8;
+    const int x = (int)(t % W); t /= W;
+    const int yy = (int)(t % H);
+    const int b = (int)(t / H);
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(res + i * 8));
+    const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[2 * k] = Half2T<DT>::to_float((uint16_t)(rw[k] & 0xFFFF));
+      v[2 * k + 1] = Half2T<DT>::to_float((uint16_t)(rw[k] >> 16));
+    }
+    if (se) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(se + (size_t)b * C + c));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(se + (size_t)b * C + c + 4));
+      v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
+      v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+    }
+    if (sc) {
+      const size_t si = (((size_t)b * H * sc_stride + (size_t)yy * sc_stride) * W * sc_stride + (size_t)x * sc_stride) * C + c;
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(sc + si));
+      const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[2 * k] += Half2T<DT>::to_float((uint16_t)(qw[k] & 0xFFFF));
+        v[2 * k + 1] += Half2T<DT>::to_float((uint16_t)(qw[k] >> 16));
+      }
+    }
+    if (y) {
+      uint4 o;
+      o.x = Half2T<DT>::pack(v[0], v[1]); o.y = Half2T<DT>::pack(v[2], v[3]);
+      o.z = Half2T<DT>::pack(v[4], v[5]); o.w = Half2T<DT>::pack(v[6], v[7]);
+      *reinterpret_cast<uint4*>(y + i * 8) = o;
+    }
+    if (yb) {
+      float a[8], d[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a[k] = s2 ? __ldg(s2 + c + k) : 1.f; d[k] = b2 ? __ldg(b2 + c + k) : 0.f; }
+      uint4 o;
+      o.x = Half2T<DT>::pack(fmaf(v[0], a[0], d[0]), fmaf(v[1], a[1], d[1]));
+      o.y = Half2T<DT>::pack(fmaf(v[2], a[2], d[2]), fmaf(v[3], a[3], d[3]));
+      o.z = Half2T<DT>::pack(fmaf(v[4], a[4], d[4]), fmaf(v[5], a[5], d[5]));
+      o.w = Half2T<DT>::pack(fmaf(v[6], a[6], d[6]), fmaf(v[7], a[7], d[7]));
+      *reinterpret_cast<uint4*>(yb + i * 8) = o;
+    }
+  }
+}
+
 int launch_scale_add(const void* res16, const float* se, const void* shortcut16, int sc_stride, const float* s2,
                      const float* b2, void* y16, void* y16b, int B, int H, int W, int C, int dtype, cudaStream_t st) {
   HF_REQUIRE(res16 && (y16 || y16b), "scale_add: null pointer");
   HF_REQUIRE(C % 2 == 0 && (sc_stride == 1 || sc_stride == 2), "scale_add: bad C / stride");
+  if (C % 8 == 0) {
+    const int64_t total8 = (int64_t)B * H * W * C / 8;
+    const int grid8 = (int)std::min<int64_t>((total8 + 255) / 256, (int64_t)num_sms() * 16);
+    if (dtype == HF_BF16)
+      scale_add_vec8_kernel<HF_BF16><<<grid8, 256, 0, st>>>((const uint16_t*)res16, se, (const uint16_t*)shortcut16,
+                                                            sc_stride, s2, b2, (uint16_t*)y16, (uint16_t*)y16b, H, W,
+                                                            C / 8, total8);
+    else
+      scale_add_vec8_kernel<HF_F16><<<grid8, 256, 0, st>>>((const uint16_t*)res16, se, (const uint16_t*)shortcut16,
+                                                           sc_stride, s2, b2, (uint16_t*)y16, (uint16_t*)y16b, H, W,
+                                                           C / 8, total8);
+    HF_LAUNCH_OK("scale_add");
+    count_launch();
+    return HF_OK;
+  }
   const int64_t total2 = (int64_t)B * H * W * C / 2;
   const int grid = (int)std::min<int64_t>((total2 + 255) / 256, (int64_t)num_sms() * 16);
   if (dtype == HF_BF16)
@@ -226,9 +365,67 @@ __global__ void __launch_bounds__(256) upsample_add_kernel(const uint16_t* __res
   }
 }
 
+template <int DT>
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    f[2 * k] = Half2T<DT>::to_float((uint16_t)(w[k] & 0xFFFF));
+    f[2 * k + 1] = Half2T<DT>::to_float((uint16_t)(w[k] >> 16));
+  }
+}
+
+// same arithmetic (same operation order per element), 8 channels per thread; C % 8 == 0
+template <int DT>
+__global__ void __launch_bounds__(256) upsample_add_vec8_kernel(const uint16_t* __restrict__ x,
+                                                                const uint16_t* __restrict__ y,
+                                                                uint16_t* __restrict__ out, int h, int w, int H, int W,
+                                                                int C8, int64_t total8) {
+  const int C = C8 * 8;
+  const float ry = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, rx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    int64_t t = i / C8;
+    const int X = (int)(t % W); t /= W;
+    const int Y = (int)(t % H);
+    const int b = (int)(t / H);
+    const float fy = Y * ry, fx = X * rx;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + 1 < h ? y0 + 1 : y0, x1 = x0 + 1 < w ? x0 + 1 : x0;
+    const float ly = fy - y0, lx = fx - x0;
+    const size_t base = (size_t)b * h * w * C + c;
+    float a00[8], a01[8], a10[8], a11[8], yy[8], v[8];
+    unpack8<DT>(__ldg(reinterpret_cast<const uint4*>(x + base + ((size_t)y0 * w + x0) * C)), a00);
+    unpack8<DT>(__ldg(reinterpret_cast<const uint4*>(x + base + ((size_t)y0 * w + x1) * C)), a01);
+    unpack8<DT>(__ldg(reinterpret_cast<const uint4*>(x + base + ((size_t)y1 * w + x0) * C)), a10);
+    unpack8<DT>(__ldg(reinterpret_cast<const uint4*>(x + base + ((size_t)y1 * w + x1) * C)), a11);
+    unpack8<DT>(__ldg(reinterpret_cast<const uint4*>(y + i * 8)), yy);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      v[k] = (1.f - ly) * ((1.f - lx) * a00[k] + lx * a01[k]) + ly * ((1.f - lx) * a10[k] + lx * a11[k]) + yy[k];
+    uint4 o;
+    o.x = Half2T<DT>::pack(v[0], v[1]); o.y = Half2T<DT>::pack(v[2], v[3]);
+    o.z = Half2T<DT>::pack(v[4], v[5]); o.w = Half2T<DT>::pack(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + i * 8) = o;
+  }
+}
+
 int launch_upsample_add(const void* x16, const void* y16, void* out16, int B, int h, int w, int H, int W, int C,
                         int dtype, cudaStream_t st) {
   HF_REQUIRE(x16 && y16 && out16 && C % 2 == 0, "upsample_add: bad arguments");
+  if (C % 8 == 0) {
+    const int64_t total8 = (int64_t)B * H * W * C / 8;
+    const int grid8 = (int)std::min<int64_t>((total8 + 255) / 256, (int64_t)num_sms() * 16);
+    if (dtype == HF_BF16)
+      upsample_add_vec8_kernel<HF_BF16><<<grid8, 256, 0, st>>>((const uint16_t*)x16, (const uint16_t*)y16,
+                                                               (uint16_t*)out16, h, w, H, W, C / 8, total8);
+    else
+      upsample_add_vec8_kernel<HF_F16><<<grid8, 256, 0, st>>>((const uint16_t*)x16, (const uint16_t*)y16,
+                                                              (uint16_t*)out16, h, w, H, W, C / 8, total8);
+    HF_LAUNCH_OK("upsample_add");
+    count_launch();
+    return HF_OK;
+  }
   const int64_t total2 = (int64_t)B * H * W * C / 2;
   const int grid = (int)std::min<int64_t>((total2 + 255) / 256, (int64_t)num_sms() * 16);
   if (dtype == HF_BF16)
@@ -261,9 +458,56 @@ __global__ void __launch_bounds__(256) adaptive_avgpool_kernel(const uint16_t* _
   }
 }
 
+// same, one CTA per (64-channel slab, output bin, sample): 8 lanes of 8 channels (16-byte loads) x 32 window pixels
+// in flight, fixed-order shared-memory reduction.  C % 8 == 0.
+template <int DT>
+__global__ void __launch_bounds__(256) adaptive_avgpool_vec8_kernel(const uint16_t* __restrict__ x,
+                                                                    float* __restrict__ y, int H, int W, int C, int oh,
+                                                                    int ow) {
+  __shared__ float red[32][65];
+  const int b = blockIdx.z, oy = blockIdx.y / ow, ox = blockIdx.y % ow, c0 = blockIdx.x * 64;
+  const int lane8 = threadIdx.x & 7, row = threadIdx.x >> 3;
+  const int c = c0 + lane8 * 8;
+  const int ys = (oy * H) / oh, ye = ((oy + 1) * H + oh - 1) / oh;
+  const int xs = (ox * W) / ow, xe = ((ox + 1) * W + ow - 1) / ow;
+  const int ww = xe - xs, n = (ye - ys) * ww;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    for (int p = row; p < n; p += 32) {
+      const int yy = ys + p / ww, xx = xs + p % ww;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + yy) * W + xx) * C + c));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[2 * k] += Half2T<DT>::to_float((uint16_t)(w[k] & 0xFFFF));
+        acc[2 * k + 1] += Half2T<DT>::to_float((uint16_t)(w[k] >> 16));
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[row][lane8 * 8 + k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < 64 && c0 + threadIdx.x < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t += red[r][threadIdx.x];
+    y[(((size_t)b * C + c0 + threadIdx.x) * oh + oy) * ow + ox] = t / (float)n;
+  }
+}
+
 int launch_adaptive_avgpool(const void* x16, float* y, int B, int H, int W, int C, int oh, int ow, int dtype,
                             cudaStream_t st) {
   HF_REQUIRE(x16 && y && oh > 0 && ow > 0, "adaptive_avgpool: bad arguments");
+  if (C % 8 == 0 && (int64_t)oh * ow <= 65535 && B <= 65535) {
+    dim3 grid(cdiv_i(C, 64), oh * ow, B);
+    if (dtype == HF_BF16)
+      adaptive_avgpool_vec8_kernel<HF_BF16><<<grid, 256, 0, st>>>((const uint16_t*)x16, y, H, W, C, oh, ow);
+    else
+      adaptive_avgpool_vec8_kernel<HF_F16><<<grid, 256, 0, st>>>((const uint16_t*)x16, y, H, W, C, oh, ow);
+    HF_LAUNCH_OK("adaptive_avgpool");
+    count_launch();
+    return HF_OK;
+  }
   const int64_t total = (int64_t)B * oh * ow * C;
   const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
   if (dtype == HF_BF16)

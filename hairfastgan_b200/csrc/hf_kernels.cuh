@@ -58,7 +58,9 @@ int launch_pack_conv2d(const float* w, const float* out_scale, void* wpk, int co
 int launch_nchw_to_nhwc16(const float* x, const float* scale, const float* shift, void* y16, int B, int C, int Cpad,
                           int HW, int dtype, cudaStream_t st);
 int launch_nhwc16_to_nchw(const void* x16, float* y, int B, int C, int HW, int dtype, cudaStream_t st);
-int launch_channel_mean(const void* x16, float* mean, int B, int HW, int C, int dtype, cudaStream_t st);
+int channel_reduce_splits(int B, int HW, int C);
+int launch_se_gate(const void* x16, const float* fc1, const float* fc2, float* out, float* ws, int B, int HW, int C,
+                   int Cr, int dtype, cudaStream_t st);
 int launch_scale_add(const void* res16, const float* se, const void* shortcut16, int sc_stride, const float* s2,
                      const float* b2, void* y16, void* y16b, int B, int H, int W, int C, int dtype, cudaStream_t st);
 int launch_upsample_add(const void* x16, const void* y16, void* out16, int B, int h, int w, int H, int W, int C,

@@ -68,10 +68,7 @@ class _PackedIRBlock:
         res, _, _ = self.conv2(h, shift=self.out_shift)
         se = None
         if self.se is not None:                                 # SEModule (helpers.py:57-75)
-            m = nn16.channel_mean(res)
-            c = m.shape[1]
-            z = F.relu(F.linear(m, self.se.fc1.weight.view(-1, c)))
-            se = torch.sigmoid(F.linear(z, self.se.fc2.weight.view(c, -1)))
+            se = nn16.se_gate(res, self.se.fc1.weight, self.se.fc2.weight)
         return nn16.scale_add(res, se, shortcut, sc_stride, next_affine, want_y16=want_raw)
 
 

@@ -111,9 +111,22 @@ def channel_mean(x16: torch.Tensor, dtype: Optional[int] = None):
     dt = default_dtype() if dtype is None else dtype
     b, h, w, c = x16.shape
     m = torch.empty(b, c, device=x16.device, dtype=torch.float32)
-    _lib.check(_lib.lib().hf_channel_mean_nhwc16(x16.data_ptr(), m.data_ptr(), b, h * w, c, dt, _lib.stream_ptr()),
-               "hf_channel_mean_nhwc16")
+    ws = torch.empty(_lib.lib().hf_channel_reduce_workspace_bytes(b, h * w, c), device=x16.device, dtype=torch.uint8)
+    _lib.check(_lib.lib().hf_channel_mean_nhwc16(x16.data_ptr(), m.data_ptr(), ws.data_ptr(), b, h * w, c, dt,
+                                                 _lib.stream_ptr()), "hf_channel_mean_nhwc16")
     return m
+
+
+def se_gate(x16: torch.Tensor, fc1_weight: torch.Tensor, fc2_weight: torch.Tensor, dtype: Optional[int] = None):
+    """SEModule gate (helpers.py:57-75) of an NHWC 16-bit tensor: [B,C] fp32."""
+    dt = default_dtype() if dtype is None else dtype
+    b, h, w, c = x16.shape
+    w1, w2 = _f32(fc1_weight).reshape(-1, c), _f32(fc2_weight).reshape(c, -1)
+    gate = torch.empty(b, c, device=x16.device, dtype=torch.float32)
+    ws = torch.empty(_lib.lib().hf_channel_reduce_workspace_bytes(b, h * w, c), device=x16.device, dtype=torch.uint8)
+    _lib.check(_lib.lib().hf_se_gate_nhwc16(x16.data_ptr(), w1.data_ptr(), w2.data_ptr(), gate.data_ptr(), ws.data_ptr(),
+                                            b, h * w, c, w1.shape[0], dt, _lib.stream_ptr()), "hf_se_gate_nhwc16")
+    return gate
 
 
 def scale_add(res16, se=None, shortcut16=None, shortcut_stride: int = 1, y16b_affine=None, want_y16: bool = True,

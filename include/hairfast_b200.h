@@ -235,8 +235,15 @@ int hf_nchw_to_nhwc16(const float* x, const float* scale, const float* shift, vo
 /* x16 [B,H,W,C] 16-bit NHWC -> y [B,C,H,W] fp32 NCHW */
 int hf_nhwc16_to_nchw(const void* x16, float* y, int batch, int channels, int height, int width, int dtype,
                       void* stream);
-/* SEModule.avg_pool (helpers.py:60): mean over H*W -> [B,C] fp32 */
-int hf_channel_mean_nhwc16(const void* x16, float* mean, int batch, int hw, int channels, int dtype, void* stream);
+/* Scratch (bytes) for the two-stage deterministic channel reduction below. */
+size_t hf_channel_reduce_workspace_bytes(int batch, int hw, int channels);
+/* SEModule.avg_pool (helpers.py:60): mean over H*W -> [B,C] fp32.  channels % 8 == 0. */
+int hf_channel_mean_nhwc16(const void* x16, float* mean, void* workspace, int batch, int hw, int channels, int dtype,
+                           void* stream);
+/* Whole SEModule gate (helpers.py:57-75): gate[b,c] = sigmoid(fc2 . relu(fc1 . mean_hw(x)));
+ * fc1_weight [reduced, channels], fc2_weight [channels, reduced] fp32 (the bias-free 1x1 convs). */
+int hf_se_gate_nhwc16(const void* x16, const float* fc1_weight, const float* fc2_weight, float* gate, void* workspace,
+                      int batch, int hw, int channels, int reduced, int dtype, void* stream);
 /* bottleneck_IR_SE tail (helpers.py:117-120): out = res * se[b,c] + shortcut[b, y*s, x*s, c];
  * se / shortcut16 / y16 / y16b may be NULL; y16b = out * s2[c] + b2[c] */
 int hf_scale_add_nhwc16(const void* res16, const float* se, const void* shortcut16, int shortcut_stride,

@@ -72,6 +72,21 @@ def test_glue_kernels(N):
     out, _ = N.scale_add(x16, se.cuda(), b16, 2)
     ref = xr * se.view(2, 64, 1, 1) + N.to_nchw32(b16).cpu()[:, :, ::2, ::2]
     assert float((N.to_nchw32(out).cpu() - ref).abs().max()) < 3e-2
+    # whole SEModule gate (helpers.py:57-75) incl. the multi-split reduction path (large H*W) and y16b output
+    for (b, c, r) in [(2, 64, 16), (3, 128, 64), (12, 64, 128)]:
+        x = torch.randn(b, c, r, r, generator=g)
+        x16 = N.to_nhwc16(x.cuda())
+        xr = N.to_nchw32(x16).cpu()
+        w1, w2 = torch.randn(c // 16, c, 1, 1, generator=g) * 0.3, torch.randn(c, c // 16, 1, 1, generator=g) * 0.3
+        m = xr.mean((2, 3))
+        ref = torch.sigmoid(F.linear(F.relu(F.linear(m, w1.view(-1, c))), w2.view(c, -1)))
+        assert float((N.se_gate(x16, w1.cuda(), w2.cuda()).cpu() - ref).abs().max()) < 1e-5
+        assert float((N.channel_mean(x16).cpu() - m).abs().max()) < 1e-5
+        s2, b2 = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
+        out, outb = N.scale_add(x16, ref.cuda(), None, 1, (s2.cuda(), b2.cuda()))
+        o = xr * ref.view(b, c, 1, 1)
+        assert float((N.to_nchw32(out).cpu() - o).abs().max()) < 3e-2
+        assert float((N.to_nchw32(outb).cpu() - (o * s2.view(1, c, 1, 1) + b2.view(1, c, 1, 1))).abs().max()) < 6e-2
 
 
 def test_e4e_encoder_golden(N, golden_dir):
