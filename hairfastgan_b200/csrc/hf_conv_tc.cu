@@ -107,7 +107,10 @@ __device__ __forceinline__ void fill_table(const ConvKernelParams& p, TableEntry
     if (p.epi == 1) {            // encoder: {scale, shift, slope, -, s2, b2}
       if (p.enc_scale) t.d = __ldg(p.enc_scale + o);
       if (p.enc_shift) t.bias = __ldg(p.enc_shift + o);
-      t.s_next = p.enc_slope ? __ldg(p.enc_slope + o) : p.enc_slope0;
+      // negative-side slope of the activation: none -> 1, PReLU -> per channel, LeakyReLU -> constant, ReLU -> 0
+      t.s_next = p.enc_act == 0 ? 1.f
+                 : p.enc_act == 3 ? 0.f
+                 : (p.enc_act == 1 && p.enc_slope) ? __ldg(p.enc_slope + o) : p.enc_slope0;
       t.w0 = p.enc_s2 ? __ldg(p.enc_s2 + o) : 1.f;
       t.w1 = p.enc_b2 ? __ldg(p.enc_b2 + o) : 0.f;
     } else if (eb < p.B) {
@@ -121,6 +124,7 @@ __device__ __forceinline__ void fill_table(const ConvKernelParams& p, TableEntry
         t.w1 = __ldg(p.rgb_w + p.Cout + o) * rs;
         t.w2 = __ldg(p.rgb_w + 2 * p.Cout + o) * rs;
       }
+      if (p.act) { t.d *= kSqrt2; t.bias *= kSqrt2; }       // lrelu(a)*sqrt2 == lrelu(a*sqrt2)
     }
     table[e] = t;
   }
@@ -143,6 +147,53 @@ __device__ __forceinline__ float4 load_noise(const ConvKernelParams& p, int b, i
   return nz;
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+// 32 accumulator columns of one pixel through the encoder epilogue, 8 columns (one 16-byte store) at a time.
+// Table entry = {scale, shift, slope, -, s2, b2, -, -}; the activation is a > 0 ? a : a*slope with slope = 1 (none)
+// / 0 (ReLU) / per-channel (PReLU) / constant (LeakyReLU), so there is no per-element branch.
+template <int DT, bool RES, bool Y16B, bool NCHW>
+__device__ __forceinline__ void epi_chunk_enc(uint32_t ts, const uint32_t (&acc)[32], const uint4* res, uint4* dst,
+                                              uint4* dst_b, float* onchw, size_t plane_o) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t rw[4] = {0u, 0u, 0u, 0u};
+    if (RES) {
+      if (res) {
+        const uint4 r = __ldg(res + g);
+        rw[0] = r.x; rw[1] = r.y; rw[2] = r.z; rw[3] = r.w;
+      }
+    }
+    uint32_t pk[4], pkb[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float v[2], vb[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = g * 8 + h * 2 + u;
+        const float4 ta = lds128(ts + (uint32_t)j * 32u);
+        float a = fmaf(__uint_as_float(acc[j]), ta.x, ta.y);
+        a = fmaf(fminf(a, 0.f), ta.z, fmaxf(a, 0.f));
+        if (RES) a += Half2T<DT>::to_float((uint16_t)(u ? (rw[h] >> 16) : (rw[h] & 0xFFFFu)));
+        if (NCHW) { if (onchw) onchw[(size_t)j * plane_o] = a; }
+        v[u] = a;
+        if (Y16B) {
+          const float4 tb = lds128(ts + (uint32_t)j * 32u + 16u);
+          vb[u] = fmaf(a, tb.x, tb.y);
+        }
+      }
+      pk[h] = Half2T<DT>::pack(v[0], v[1]);
+      if (Y16B) pkb[h] = Half2T<DT>::pack(vb[0], vb[1]);
+    }
+    if (dst) dst[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    if (Y16B) { if (dst_b) dst_b[g] = make_uint4(pkb[0], pkb[1], pkb[2], pkb[3]); }
+  }
+}
+
 // Encoder epilogue (plain conv + folded BatchNorm / bias + PReLU | LeakyReLU | ReLU + residual):
 //   v = act(acc*scale[o] + shift[o]) + residual ; y16 = v ; y16b = v*s2[o] + b2[o] ; y32 (NCHW) = v
 // (reference: bottleneck_IR_SE / IBasicBlock conv stacks, encoder4editing/models/encoders/helpers.py:98-120,
@@ -153,6 +204,8 @@ __device__ __forceinline__ void epilogue_tile_enc(const ConvKernelParams& p, con
   const int chunks = p.n_tile / 32;
   const size_t plane_o = (size_t)p.Ho * p.Wo;
   const size_t pix = valid ? ((size_t)b * p.Ho + y) * p.Wo + x : 0;
+  const uint32_t trow_s = smem_u32(trow);
+  const int variant = p.out_nchw ? 3 : ((p.enc_residual ? 1 : 0) | (p.enc_y16b ? 2 : 0));
   for (int q = 0; q < chunks; ++q) {
     uint32_t acc[32];
     tmem_ld_32x32(taddr + q * 32, acc);
@@ -162,55 +215,58 @@ __device__ __forceinline__ void epilogue_tile_enc(const ConvKernelParams& p, con
       if (REMOTE_RELEASE) mbar_arrive_leader(release_bar); else mbar_arrive(release_bar);
     }
     const int o_base = n0 + q * 32;
-    uint32_t res[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) res[i] = 0u;
-    if (p.enc_residual && valid) {
-      const uint4* rp = reinterpret_cast<const uint4*>(p.enc_residual + pix * p.Cout + o_base);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint4 r = __ldg(rp + i);
-        res[4 * i] = r.x; res[4 * i + 1] = r.y; res[4 * i + 2] = r.z; res[4 * i + 3] = r.w;
-      }
-    }
+    const size_t eo = pix * p.Cout + o_base;
+    const uint4* res = (p.enc_residual && valid) ? reinterpret_cast<const uint4*>(p.enc_residual + eo) : nullptr;
+    uint4* dst = (p.xhat_out && valid) ? reinterpret_cast<uint4*>(p.xhat_out + eo) : nullptr;
+    uint4* dst_b = (p.enc_y16b && valid) ? reinterpret_cast<uint4*>(p.enc_y16b + eo) : nullptr;
     float* onchw = (p.out_nchw && valid) ? p.out_nchw + ((size_t)b * p.Cout + o_base) * plane_o + (size_t)y * p.Wo + x
                                          : nullptr;
-    uint32_t packed[16], packed_b[16];
+    const uint32_t ts = trow_s + (uint32_t)(q * 32) * (uint32_t)sizeof(TableEntry);
+    switch (variant) {       // uniform across the CTA
+      case 0: epi_chunk_enc<DT, false, false, false>(ts, acc, res, dst, dst_b, onchw, plane_o); break;
+      case 1: epi_chunk_enc<DT, true, false, false>(ts, acc, res, dst, dst_b, onchw, plane_o); break;
+      case 2: epi_chunk_enc<DT, false, true, false>(ts, acc, res, dst, dst_b, onchw, plane_o); break;
+      default: epi_chunk_enc<DT, true, true, true>(ts, acc, res, dst, dst_b, onchw, plane_o); break;
+    }
+  }
+}
+
+// 32 accumulator columns of one pixel through the StyledConv epilogue, 8 columns (one 16-byte store) at a time.
+// `ts` = shared-window address of the table entry of column 0 (LDS.128, broadcast across the warp).  RGB:
+// accumulate the fused ToRGB dot products; NCHW: also store the fp32 activation (feature outputs / module-level
+// API); XOUT: produce the 16-bit operand of the next conv.
+template <int DT, bool RGB, bool NCHW, bool XOUT>
+__device__ __forceinline__ void epi_chunk(uint32_t ts, const uint32_t (&acc)[32], float nzv, float slope, uint4* dst,
+                                          float& r0, float& r1, float& r2, float* onchw, size_t plane_o) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      float v[2], vb[2];
+  for (int g = 0; g < 4; ++g) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float v[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const TableEntry& t = trow[q * 32 + j + u];
-        float a = fmaf(__uint_as_float(acc[j + u]), t.d, t.bias);
-        if (p.enc_act == 1 || p.enc_act == 2) a = a > 0.f ? a : a * t.s_next;
-        else if (p.enc_act == 3) a = fmaxf(a, 0.f);
-        a += Half2T<DT>::to_float((uint16_t)(u ? (res[j >> 1] >> 16) : (res[j >> 1] & 0xFFFFu)));
-        if (onchw) onchw[(size_t)(j + u) * plane_o] = a;
-        v[u] = a;
-        vb[u] = fmaf(a, t.w0, t.w1);
+        const int j = g * 8 + h * 2 + u;
+        const float4 ta = lds128(ts + (uint32_t)j * 32u);            // d, bias, s_next, -
+        float a = fmaf(__uint_as_float(acc[j]), ta.x, nzv + ta.y);
+        a = fmaxf(a, slope * a);
+        if (RGB) {
+          const float4 tb = lds128(ts + (uint32_t)j * 32u + 16u);    // ToRGB weights * style
+          r0 = fmaf(a, tb.x, r0); r1 = fmaf(a, tb.y, r1); r2 = fmaf(a, tb.z, r2);
+        }
+        if (NCHW) { if (onchw) onchw[(size_t)j * plane_o] = a; }
+        v[u] = a * ta.z;
       }
-      packed[j >> 1] = Half2T<DT>::pack(v[0], v[1]);
-      packed_b[j >> 1] = Half2T<DT>::pack(vb[0], vb[1]);
+      if (XOUT) pk[h] = Half2T<DT>::pack(v[0], v[1]);
     }
-    if (p.xhat_out && valid) {
-      uint4* dst = reinterpret_cast<uint4*>(p.xhat_out + pix * p.Cout + o_base);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-    }
-    if (p.enc_y16b && valid) {
-      uint4* dst = reinterpret_cast<uint4*>(p.enc_y16b + pix * p.Cout + o_base);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        dst[i] = make_uint4(packed_b[4 * i], packed_b[4 * i + 1], packed_b[4 * i + 2], packed_b[4 * i + 3]);
-    }
+    if (XOUT) { if (dst) dst[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]); }
   }
 }
 
 // TMEM -> registers -> fused epilogue -> global, for one tile and one thread (= one GEMM row = one pixel).
 //   a = acc*d + nw*noise + bias ; a = lrelu(a)*sqrt2 ; rgb += a*wrgb ; out16 = a*s_next
 // `release_bar` != nullptr: arrive on it right after the last TMEM read (hands the accumulator back).
+// The fused ToRGB partial sums exist for plain (non-upsampling) convolutions only (launch_conv checks).
 template <int DT, bool REMOTE_RELEASE = false>
 __device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, const TableEntry* trow, uint32_t taddr,
                                               uint64_t* release_bar, int n0, int nt, int b, int y, int x, bool valid,
@@ -221,9 +277,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, const T
   }
   const int chunks = p.n_tile / 32;
   const size_t plane_o = (size_t)p.Ho * p.Wo;
-  float rgb[4][3];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) rgb[i][0] = rgb[i][1] = rgb[i][2] = 0.f;
+  float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+  // the table already carries d*sqrt2 / bias*sqrt2 when the activation is on (fill_table): lrelu(a)*sqrt2 =
+  // max(a', 0.2 a') with a' = a*sqrt2; slope 1 turns the max into the identity
+  const float slope = p.act ? 0.2f : 1.f, nscale = p.act ? kSqrt2 : 1.f;
+  const uint32_t trow_s = smem_u32(trow);
+  const int variant = (p.rgb_partial ? 1 : 0) | (p.out_nchw ? 2 : 0) | (p.xhat_out ? 4 : 0);
 
   for (int q = 0; q < chunks; ++q) {
     uint32_t acc[32];
@@ -238,46 +297,24 @@ __device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, const T
     const int o_base = (p.up ? (n0 >> 2) : n0) + t_base;
     const int yo = p.up ? 2 * y + (par >> 1) : y;
     const int xo = p.up ? 2 * x + (par & 1) : x;
-    const float nzv = par == 0 ? nz.x : (par == 1 ? nz.y : (par == 2 ? nz.z : nz.w));
-    uint32_t packed[16];
-    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    const float nzv = nscale * (par == 0 ? nz.x : (par == 1 ? nz.y : (par == 2 ? nz.z : nz.w)));
     float* onchw = (p.out_nchw && valid) ? p.out_nchw + ((size_t)b * p.Cout + o_base) * plane_o +
                                               (size_t)yo * p.Wo + xo
                                             : nullptr;
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      float v[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const TableEntry& t = trow[t_base + j + u];
-        float a = fmaf(__uint_as_float(acc[j + u]), t.d, nzv + t.bias);
-        if (p.act) a = (a > 0.f ? a : 0.2f * a) * kSqrt2;
-        r0 = fmaf(a, t.w0, r0); r1 = fmaf(a, t.w1, r1); r2 = fmaf(a, t.w2, r2);
-        if (onchw) onchw[(size_t)(j + u) * plane_o] = a;
-        v[u] = a * t.s_next;
-      }
-      packed[j >> 1] = Half2T<DT>::pack(v[0], v[1]);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (i == par) { rgb[i][0] += r0; rgb[i][1] += r1; rgb[i][2] += r2; }
-    if (p.xhat_out && valid) {
-      uint4* dst = reinterpret_cast<uint4*>(p.xhat_out + (((size_t)b * p.Ho + yo) * p.Wo + xo) * p.Cout + o_base);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+    uint4* dst = (p.xhat_out && valid)
+                     ? reinterpret_cast<uint4*>(p.xhat_out + (((size_t)b * p.Ho + yo) * p.Wo + xo) * p.Cout + o_base)
+                     : nullptr;
+    const uint32_t ts = trow_s + (uint32_t)t_base * (uint32_t)sizeof(TableEntry);
+    switch (variant) {     // uniform across the CTA; one specialised, fully unrolled body per combination
+      case 4: epi_chunk<DT, false, false, true>(ts, acc, nzv, slope, dst, r0, r1, r2, onchw, plane_o); break;
+      case 5: epi_chunk<DT, true, false, true>(ts, acc, nzv, slope, dst, r0, r1, r2, onchw, plane_o); break;
+      case 1: epi_chunk<DT, true, false, false>(ts, acc, nzv, slope, dst, r0, r1, r2, onchw, plane_o); break;
+      default: epi_chunk<DT, true, true, true>(ts, acc, nzv, slope, dst, r0, r1, r2, onchw, plane_o); break;
     }
   }
   if (p.rgb_partial && valid) {
-    float* pp = p.rgb_partial + ((size_t)nt * p.B + b) * 3 * plane_o;
-#pragma unroll
-    for (int par = 0; par < 4; ++par) {
-      if (par > 0 && !p.up) break;
-      const int yo = p.up ? 2 * y + (par >> 1) : y;
-      const int xo = p.up ? 2 * x + (par & 1) : x;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) pp[(size_t)j * plane_o + (size_t)yo * p.Wo + xo] = rgb[par][j];
-    }
+    float* pp = p.rgb_partial + ((size_t)nt * p.B + b) * 3 * plane_o + (size_t)y * p.Wo + x;
+    pp[0] = r0; pp[plane_o] = r1; pp[2 * plane_o] = r2;
   }
 }
 
@@ -1005,6 +1042,7 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st, ConvPlan* plan_out) {
   if (rc) return rc;
   HF_REQUIRE(a.xhat_in && a.wpk, "conv: null operand pointer");
   HF_REQUIRE(!a.rgb_partial || (a.rgb_w && a.rgb_s), "conv: rgb_partial needs rgb_w and rgb_s");
+  HF_REQUIRE(!a.rgb_partial || !a.up, "conv: the fused ToRGB partial sums exist for non-upsampling convs only");
   HF_REQUIRE(!a.noise || a.noise_w, "conv: noise given without noise weight");
   HF_REQUIRE((((uintptr_t)a.xhat_in | (uintptr_t)a.wpk | (uintptr_t)a.xhat_out) & 15) == 0,
              "conv: 16-bit tensors must be 16-byte aligned");
