@@ -66,6 +66,7 @@ struct ConvKernelParams {
   float* rgb_partial;
   // plain (encoder) convolution: epi == 1 -> v = act(acc*scale[o] + shift[o]) + residual;
   // y16 (= xhat_out) = v ; y16b = v*s2[o] + b2[o] ; out_nchw = v
+  int dbg;
   int epi, stride, cin_g, cout_g, enc_act;
   float enc_slope0;
   const float* enc_scale;
@@ -130,7 +131,8 @@ __device__ __forceinline__ void fill_table(const ConvKernelParams& p, TableEntry
   }
 }
 
-// nw * noise for one pixel (plain: .x) or its 2x2 output quad (up: x,y = top row; z,w = bottom row)
+// raw noise for one pixel (plain: .x) or its 2x2 output quad (up: x,y = top row; z,w = bottom row); the caller
+// multiplies by the noise weight when the value is USED, so the load can stay in flight behind other work
 __device__ __forceinline__ float4 load_noise(const ConvKernelParams& p, int b, int y, int x, float nw) {
   float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p.noise) {
@@ -139,9 +141,9 @@ __device__ __forceinline__ float4 load_noise(const ConvKernelParams& p, int b, i
       const float* r0 = np_ + (size_t)(2 * y) * p.Wo + 2 * x;
       const float2 a = __ldg(reinterpret_cast<const float2*>(r0));
       const float2 c = __ldg(reinterpret_cast<const float2*>(r0 + p.Wo));
-      nz = make_float4(nw * a.x, nw * a.y, nw * c.x, nw * c.y);
+      nz = make_float4(a.x, a.y, c.x, c.y);
     } else {
-      nz.x = nw * __ldg(np_ + (size_t)y * p.Wo + x);
+      nz.x = __ldg(np_ + (size_t)y * p.Wo + x);
     }
   }
   return nz;
@@ -270,7 +272,7 @@ __device__ __forceinline__ void epi_chunk(uint32_t ts, const uint32_t (&acc)[32]
 template <int DT, bool REMOTE_RELEASE = false>
 __device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, const TableEntry* trow, uint32_t taddr,
                                               uint64_t* release_bar, int n0, int nt, int b, int y, int x, bool valid,
-                                              float4 nz) {
+                                              float4 nz, float nw) {
   if (p.epi == 1) {
     epilogue_tile_enc<DT, REMOTE_RELEASE>(p, trow, taddr, release_bar, n0, b, y, x, valid);
     return;
@@ -280,7 +282,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, const T
   float r0 = 0.f, r1 = 0.f, r2 = 0.f;
   // the table already carries d*sqrt2 / bias*sqrt2 when the activation is on (fill_table): lrelu(a)*sqrt2 =
   // max(a', 0.2 a') with a' = a*sqrt2; slope 1 turns the max into the identity
-  const float slope = p.act ? 0.2f : 1.f, nscale = p.act ? kSqrt2 : 1.f;
+  const float slope = p.act ? 0.2f : 1.f, nscale = (p.act ? kSqrt2 : 1.f) * nw;
   const uint32_t trow_s = smem_u32(trow);
   const int variant = (p.rgb_partial ? 1 : 0) | (p.out_nchw ? 2 : 0) | (p.xhat_out ? 4 : 0);
 
@@ -292,6 +294,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, const T
       tc_fence_before();
       if (REMOTE_RELEASE) mbar_arrive_leader(release_bar); else mbar_arrive(release_bar);
     }
+    if (p.dbg & 1) { r0 += __uint_as_float(acc[0]); continue; }
     const int par = p.up ? (q & 3) : 0;
     const int t_base = p.up ? (q >> 2) * 32 : q * 32;          // channel offset inside the tile
     const int o_base = (p.up ? (n0 >> 2) : n0) + t_base;
@@ -453,7 +456,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * 256);
-      epilogue_tile<DT>(p, table + (p.epi == 1 ? 0 : bb * nc_tile), taddr, &tmem_empty[buf], n0, nt, b, y, x, valid, nz);
+      epilogue_tile<DT>(p, table + (p.epi == 1 ? 0 : bb * nc_tile), taddr, &tmem_empty[buf], n0, nt, b, y, x, valid, nz, nw);
     }
   }
 
@@ -689,7 +692,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           cached_bt = cur.bt; cached_nt = nt;
         }
         epilogue_tile<DT>(p, my_table, taddr + (uint32_t)(g * p.n_tile), g == gcount - 1 ? &tmem_empty[grp] : nullptr,
-                          n0, nt, cur.bt, cur.y0 + h_l, cur.x0 + w_l, true, nz);
+                          n0, nt, cur.bt, cur.y0 + h_l, cur.x0 + w_l, true, nz, nw);
       }
     }
   }
@@ -857,7 +860,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * 256);
       // hand the accumulator back to the LEADER's barrier (remote arrive from the peer CTA)
-      epilogue_tile<DT, true>(p, my_table, taddr, &tmem_empty[grp], n0, nt, tc.bt, tc.y0 + h_l, tc.x0 + w_l, true, nz);
+      epilogue_tile<DT, true>(p, my_table, taddr, &tmem_empty[grp], n0, nt, tc.bt, tc.y0 + h_l, tc.x0 + w_l, true, nz, nw);
     }
   }
 
@@ -1099,6 +1102,7 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st, ConvPlan* plan_out) {
   kp.rgb_w = a.rgb_partial ? a.rgb_w : nullptr;
   kp.rgb_s = a.rgb_s;
   kp.rgb_partial = a.rgb_partial;
+  kp.dbg = env_int("HF_CONV_DBG", 0);       // experiments only: 1 = epilogue reduced to the TMEM read + release
   kp.epi = a.epi; kp.stride = stride; kp.cin_g = cin_g;
   kp.cout_g = (a.up ? 4 * a.Cout : a.Cout) / groups;
   kp.enc_act = a.enc_act; kp.enc_slope0 = a.enc_slope0;
