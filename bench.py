@@ -298,7 +298,26 @@ def cpu_oracle_sample(threads=None):
     return dt, frac / dt, torch.get_num_threads()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, ...) write to fd 1 from C, so
+    point fd 1 at stderr for the whole run and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -327,7 +346,7 @@ def main():
                 times.append(dt)
         dt = sum(times) / len(times)
         val = ((GFLOP_FULL + GFLOP_E4E_IMG + GFLOP_FSE_IMG) / GFLOP_PER_TRIPLE) / dt
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": "hair_swap_triples_per_sec", "value": val, "unit": "triples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -365,7 +384,7 @@ def main():
         dt, tps, thr = cpu_oracle_sample()
         out["cpu_baseline"] = {"value": round(tps, 5), "unit": "triples/s", "cores": thr, "kind": "port",
                                "sample": f"oracle generator_ref + e4e_ref + fse_ref, B=1 ({dt:.1f} s): " + sample}
-    print(json.dumps(out))
+    emit(out)
 
 
 if __name__ == "__main__":
