@@ -309,38 +309,46 @@ class fs_encoder_v2(nn.Module):
             nn.BatchNorm2d(256, eps=1e-05), nn.Conv2d(256, 512, kernel_size=3, stride=1, padding=1, bias=False),
             nn.BatchNorm2d(512, eps=1e-05), nn.PReLU(num_parameters=512),
             nn.Conv2d(512, 512, kernel_size=3, stride=s, padding=1, bias=False), nn.BatchNorm2d(512, eps=1e-05))
-        self._content_stride = s
+        self._content_stage = 2                    # the content branch taps the block_3 output
+        self._content_strides = [s]
         self.avg_pool = nn.AdaptiveAvgPool2d((3, 3))
         self.styles = nn.ModuleList([nn.Linear(960 * 9, 512) for _ in range(n_styles)])
         self._pk = None
+
+    def _content_branches(self):
+        """[(BN, conv3x3, BN, PReLU, conv3x3(stride), BN)] -- one per content output."""
+        return [self.content_layer]
 
     def _pack(self):
         key = _params_key(self)
         if self._pk is not None and self._pk["key"] == key:
             return self._pk
         sc, sh = nn16.bn_affine(self.conv[1])
-        cl = self.content_layer
-        c_mid_scale, c_mid_shift = nn16.bn_affine(cl[2])
-        c_out_scale, c_out_shift = nn16.bn_affine(cl[5])
+        branches = []
+        for cl, stride in zip(self._content_branches(), self._content_strides):
+            c_mid_scale, c_mid_shift = nn16.bn_affine(cl[2])
+            c_out_scale, c_out_shift = nn16.bn_affine(cl[5])
+            branches.append({"pre": nn16.bn_affine(cl[0]),
+                             "conv1": nn16.PackedConv2d(cl[1].weight, c_mid_scale), "shift1": c_mid_shift,
+                             "slope": cl[3].weight.detach().float().contiguous(),
+                             "conv2": nn16.PackedConv2d(cl[4].weight, c_out_scale, stride=stride),
+                             "shift2": c_out_shift})
         pk = {"key": key, "stem": nn16.PackedConv2d(self.conv[0].weight, sc, cin_pad=32), "stem_shift": sh,
               "stem_slope": self.conv[2].weight.detach().float().contiguous(),
               "stages": [[b.packed() for b in blk] for blk in (self.block_1, self.block_2, self.block_3, self.block_4)],
-              "content_pre": nn16.bn_affine(cl[0]),
-              "content1": nn16.PackedConv2d(cl[1].weight, c_mid_scale), "content1_shift": c_mid_shift,
-              "content_slope": cl[3].weight.detach().float().contiguous(),
-              "content2": nn16.PackedConv2d(cl[4].weight, c_out_scale, stride=self._content_stride),
-              "content2_shift": c_out_shift,
+              "content": branches,
               "style_w": torch.stack([s.weight.detach().float() for s in self.styles], 0),     # [18,512,8640]
               "style_b": torch.stack([s.bias.detach().float() for s in self.styles], 0)}
         self._pk = pk
         return pk
 
-    @torch.no_grad()
-    def forward(self, x):
+    def _trunk(self, x):
+        """conv stem -> block_1..4 with the pooled features and the content branches: (latents, [content...])."""
+        name = type(self).__name__
         if self.training:
-            raise RuntimeError("fs_encoder_v2: only eval-mode (running BatchNorm statistics) forward is implemented")
+            raise RuntimeError(f"{name}: only eval-mode (running BatchNorm statistics) forward is implemented")
         if not x.is_cuda:
-            raise RuntimeError("fs_encoder_v2: input must be a CUDA tensor (no CPU fallback)")
+            raise RuntimeError(f"{name}: input must be a CUDA tensor (no CPU fallback)")
         pk = self._pack()
         blocks = [b for st in pk["stages"] for b in st]
         ends, n = [], 0
@@ -349,16 +357,23 @@ class fs_encoder_v2(nn.Module):
             ends.append(n - 1)
         x16 = nn16.to_nhwc16(x, c_pad=32)
         raw, bn, _ = pk["stem"](x16, shift=pk["stem_shift"], act=1, slope=pk["stem_slope"], y16b_affine=blocks[0].pre)
-        feats, content = [], None
+        feats, content = [], []
         for i, blk in enumerate(blocks):
             nxt = blocks[i + 1].pre if i + 1 < len(blocks) else None
             raw, bn = blk(raw, bn, nxt, want_raw=True)
             if i in ends:
                 feats.append(nn16.adaptive_avgpool(raw, 3, 3))
-                if i == ends[2]:                                   # content branch on the stage-3 output
-                    _, cb = nn16.scale_add(raw, y16b_affine=pk["content_pre"], want_y16=False)   # content_layer[0] BN
-                    h, _, _ = pk["content1"](cb, shift=pk["content1_shift"], act=1, slope=pk["content_slope"])
-                    _, _, content = pk["content2"](h, shift=pk["content2_shift"], want_y16=False, want_y32=True)
+                if i == ends[self._content_stage]:
+                    for br in pk["content"]:
+                        _, cb = nn16.scale_add(raw, y16b_affine=br["pre"], want_y16=False)      # leading BatchNorm
+                        h, _, _ = br["conv1"](cb, shift=br["shift1"], act=1, slope=br["slope"])
+                        _, _, c = br["conv2"](h, shift=br["shift2"], want_y16=False, want_y32=True)
+                        content.append(c)
         f = torch.cat(feats, dim=1).reshape(x.shape[0], -1)                               # [B, 960*9]
         out = torch.einsum("bi,hoi->bho", f, pk["style_w"]) + pk["style_b"]                # 18 x nn.Linear(8640,512)
         return out, content
+
+    @torch.no_grad()
+    def forward(self, x):
+        out, content = self._trunk(x)
+        return out, content[0]

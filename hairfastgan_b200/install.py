@@ -17,12 +17,18 @@ After ``install()`` the import statements of the reference resolve to this packa
   ``psp_encoders.Encoder4Editing(50, 'ir_se', opts)`` :34) and ``from nets.feature_style_encoder import *``
   (FeatureStyleEncoder/trainer.py:20; ``fs_encoder_v2(...)`` :168)                  -> ``hairfastgan_b200.encoders``
 
+* ``FeatureEncoderMult`` / ``FeatureiResnet`` as ``PostProcessModel`` builds them (models/Encoders.py:106-113): the
+  names are rebound inside ``models.Net`` / ``models.Encoders`` when those modules are imported
+                                                                                    -> ``hairfastgan_b200.postprocess``
+
 Nothing in the reference tree is edited and its JIT build of the two 2019 CUDA extensions
 (op/fused_act.py:10-16, op/upfirdn2d.py:10-16) never runs.
 """
 from __future__ import annotations
 
 import importlib
+import importlib.abc
+import importlib.util
 import sys
 import types
 
@@ -43,6 +49,56 @@ _ENCODERS = {
 }
 _created_stubs = []
 
+# PostProcess conv stack.  models/Net.py and models/Encoders.py hold much more than these classes
+# (BiSeNet glue, CLIP models, ...), so the modules stay the reference's and only these names are rebound right after
+# the module body has run -- PostProcessModel.__init__ (models/Encoders.py:106-113) looks them up at call time.
+_POSTPROCESS = {
+    "models.Net": ("FeatureEncoder", "FeatureEncoderMult"),
+    "models.Encoders": ("FeatureEncoderMult", "FeatureiResnet"),
+}
+_saved_attrs = []
+
+
+def _patch_postprocess(module) -> None:
+    ours = importlib.import_module("hairfastgan_b200.postprocess")
+    for attr in _POSTPROCESS.get(module.__name__, ()):
+        if hasattr(module, attr) and getattr(module, attr) is not getattr(ours, attr):
+            _saved_attrs.append((module, attr, getattr(module, attr)))
+            setattr(module, attr, getattr(ours, attr))
+
+
+class _PatchingLoader(importlib.abc.Loader):
+    def __init__(self, inner):
+        self.inner = inner
+
+    def create_module(self, spec):
+        return self.inner.create_module(spec)
+
+    def exec_module(self, module):
+        self.inner.exec_module(module)
+        _patch_postprocess(module)
+
+
+class _PostImportPatcher(importlib.abc.MetaPathFinder):
+    """Meta-path finder that lets the normal machinery locate models.Net / models.Encoders and wraps their loader."""
+    _busy = False
+
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname not in _POSTPROCESS or _PostImportPatcher._busy:
+            return None
+        _PostImportPatcher._busy = True
+        try:
+            spec = importlib.util.find_spec(fullname)
+        finally:
+            _PostImportPatcher._busy = False
+        if spec is None or spec.loader is None:
+            return None
+        spec.loader = _PatchingLoader(spec.loader)
+        return spec
+
+
+_patcher = _PostImportPatcher()
+
 
 def _register(ref_name: str, ours: str) -> None:
     top = ref_name.split(".")[0]
@@ -58,10 +114,10 @@ def _register(ref_name: str, ours: str) -> None:
     sys.modules[ref_name] = importlib.import_module(ours)
 
 
-def install(generator: bool = True, encoders: bool = True) -> None:
+def install(generator: bool = True, encoders: bool = True, postprocess: bool = True) -> None:
     """Register the overlay.  ``generator=False`` swaps only the operator package (L1 boundary) and leaves the
     reference's own ``models/stylegan2/model.py`` classes in place on top of our ops; ``encoders=False`` keeps
-    the reference's PyTorch encoders."""
+    the reference's PyTorch encoders; ``postprocess=False`` keeps its PostProcess conv stack."""
     for ref_name, ours in _OPS.items():
         _register(ref_name, ours)
     if generator:
@@ -70,9 +126,20 @@ def install(generator: bool = True, encoders: bool = True) -> None:
     if encoders:
         for ref_name, ours in _ENCODERS.items():
             _register(ref_name, ours)
+    if postprocess:
+        if _patcher not in sys.meta_path:
+            sys.meta_path.insert(0, _patcher)
+        for name in _POSTPROCESS:                    # already imported: rebind now
+            if name in sys.modules:
+                _patch_postprocess(sys.modules[name])
 
 
 def uninstall() -> None:
     for ref_name in list(_OPS) + list(_GENERATORS) + list(_ENCODERS) + _created_stubs:
         sys.modules.pop(ref_name, None)
     _created_stubs.clear()
+    if _patcher in sys.meta_path:
+        sys.meta_path.remove(_patcher)
+    for module, attr, value in reversed(_saved_attrs):
+        setattr(module, attr, value)
+    _saved_attrs.clear()

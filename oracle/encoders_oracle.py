@@ -7,10 +7,13 @@ Functional fp32 restatements (torch CPU, no nn.Module, no reference imports) of
   (psp_encoders.py:34-55);
 * FSE ``fs_encoder_v2.forward`` -- models/FeatureStyleEncoder/nets/feature_style_encoder.py:47-65 with
   ``IBasicBlock`` (arcface/iresnet.py:28-57).
+* PostProcess conv stack: ``FeatureEncoderMult(fs_layers=[9]).forward`` -- models/Net.py:396-477 --
+  and ``FeatureiResnet.forward`` -- models/Encoders.py:35-57 -- with ``IBasicBlock`` (models/Net.py:162-190).
 BatchNorm is evaluated in eval mode (running statistics), as on the swap() path.
 
-Pinned by tests/golden/encoders.npz, produced by oracle/gen_golden_encoders.py from the unmodified
-reference classes with the same seeded synthetic parameters (``synth_*_params``; no pretrained weights exist).
+Pinned by tests/golden/encoders.npz and tests/golden/postprocess.npz, produced by oracle/gen_golden_encoders.py /
+gen_golden_postprocess.py from the unmodified reference classes with the same seeded synthetic parameters
+(``synth_params_like``; no pretrained weights exist).
 """
 from __future__ import annotations
 
@@ -114,24 +117,56 @@ def ibasic_block_ref(x: Tensor, p: Dict[str, Tensor], pre: str, stride: int, has
     return out + idt
 
 
-def fse_ref(p: Dict[str, Tensor], x: Tensor, content_stride: int = 2, n_styles: int = 18):
-    """nets/feature_style_encoder.py:47-65."""
+def fse_ref(p: Dict[str, Tensor], x: Tensor, content_stride: int = 2, n_styles: int = 18,
+            content_stage: str = "block_3", content_prefix: str = "content_layer."):
+    """nets/feature_style_encoder.py:47-65.  With ``content_stage="block_2", content_prefix="content_layer.0.",
+    content_stride=1`` this is ``FeatureEncoderMult(fs_layers=[9]).forward`` after its resize (models/Net.py:446-477:
+    max(fs_layers) > 7 taps the content branch after block_2, kernel (3,3), stride (1,1))."""
     x = F.conv2d(x, p["conv.0.weight"], padding=1)
     x = _prelu(_bn(x, p, "conv.1."), p["conv.2.weight"])
     feats, content = [], None
     for name, cin, planes, n in FSE_STAGES:
         for j in range(n):
             x = ibasic_block_ref(x, p, f"{name}.{j}.", 2 if j == 0 else 1, j == 0)
-        if name == "block_3":
-            c = _bn(x, p, "content_layer.0.")
-            c = F.conv2d(c, p["content_layer.1.weight"], padding=1)
-            c = _prelu(_bn(c, p, "content_layer.2."), p["content_layer.3.weight"])
-            c = F.conv2d(c, p["content_layer.4.weight"], stride=content_stride, padding=1)
-            content = _bn(c, p, "content_layer.5.")
+        if name == content_stage:
+            c = _bn(x, p, content_prefix + "0.")
+            c = F.conv2d(c, p[content_prefix + "1.weight"], padding=1)
+            c = _prelu(_bn(c, p, content_prefix + "2."), p[content_prefix + "3.weight"])
+            c = F.conv2d(c, p[content_prefix + "4.weight"], stride=content_stride, padding=1)
+            content = _bn(c, p, content_prefix + "5.")
         feats.append(F.adaptive_avg_pool2d(x, (3, 3)))
     f = torch.cat(feats, dim=1).view(x.size(0), -1)
     out = torch.stack([F.linear(f, p[f"styles.{i}.weight"], p[f"styles.{i}.bias"]) for i in range(n_styles)], dim=1)
     return out, content
+
+
+# ------------------------------------------------------------------------------------------------ PostProcess (8f-1)
+def transform_to_256_ref(x: Tensor) -> Tensor:
+    """models/Net.py:12-14 ``transforms.Resize((256, 256))`` on a tensor: bilinear, align_corners=False, and no
+    antialias under the reference's pinned torchvision (0.14: ``antialias=None`` -> False for tensors)."""
+    if x.shape[-2:] == (256, 256):
+        return x
+    return F.interpolate(x, size=(256, 256), mode="bilinear", align_corners=False)
+
+
+def feature_encoder_mult_ref(p: Dict[str, Tensor], x: Tensor):
+    """``FeatureEncoderMult(fs_layers=[9]).forward`` (models/Net.py:446-477) -> (latents [B,18,512], [content])."""
+    lat, content = fse_ref(p, transform_to_256_ref(x), content_stride=1, content_stage="block_2",
+                           content_prefix="content_layer.0.")
+    return lat, [content]
+
+
+PP_BLOCKS = [[1024, 2], [768, 2], [512, 2]]          # PostProcessModel.to_feature, models/Encoders.py:113
+
+
+def feature_iresnet_ref(p: Dict[str, Tensor], x: Tensor, blocks=PP_BLOCKS, inplanes: int = 1024) -> Tensor:
+    """``FeatureiResnet.forward`` (models/Encoders.py:35-57): IBasicBlocks at stride 1, a conv1x1 + BN shortcut
+    where the width changes."""
+    for n, (planes, num) in enumerate(blocks, start=1):
+        for k in range(1, num + 1):
+            x = ibasic_block_ref(x, p, f"res_blocks.res_block_{n}_{k}.", 1, inplanes != planes)
+            inplanes = planes
+    return x
 
 
 # ------------------------------------------------------------------------------------------------ synthetic parameters
@@ -158,7 +193,8 @@ def _fill(sd: Dict[str, Tensor], seed: int) -> Dict[str, Tensor]:
         elif k.endswith("bias"):
             out[k] = torch.randn(v.shape, generator=g) * 0.1
         elif v.ndim == 1 and ("prelu" in k or k.endswith("res_layer.2.weight") or k.endswith("input_layer.2.weight")
-                              or k.endswith("conv.2.weight") or k.endswith("content_layer.3.weight")):
+                              or k.endswith("conv.2.weight") or k.endswith("content_layer.3.weight")
+                              or k.endswith("content_layer.0.3.weight")):
             out[k] = torch.rand(v.shape, generator=g) * 0.3 + 0.1    # PReLU slopes
         elif k.endswith("res_layer.4.weight") or k.endswith("bn3.weight") or k.endswith("downsample.1.weight") \
                 or k.endswith("shortcut_layer.1.weight"):

@@ -122,6 +122,40 @@ def test_install_overlay_redirects_reference_imports():
     assert "models.stylegan2.op" not in sys.modules and "nets" not in sys.modules
 
 
+def test_install_rebinds_postprocess_classes(tmp_path):
+    """models.Net / models.Encoders stay the reference's modules; only the PostProcess class names are rebound,
+    right after import (a stand-in package with the same module layout plays the reference here)."""
+    import sys
+    import hairfastgan_b200.install as inst
+    import hairfastgan_b200.postprocess as P
+    pkg = tmp_path / "models"
+    pkg.mkdir()
+    (pkg / "__init__.py").write_text("")
+    (pkg / "Net.py").write_text("class FeatureEncoder: pass\nclass FeatureEncoderMult(FeatureEncoder): pass\n"
+                                "class Net: pass\n")
+    (pkg / "Encoders.py").write_text("from models.Net import FeatureEncoderMult\nclass FeatureiResnet: pass\n"
+                                     "class PostProcessModel:\n    def build(self):\n"
+                                     "        return FeatureEncoderMult, FeatureiResnet\n")
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "models" or k.startswith("models.")}
+    sys.path.insert(0, str(tmp_path))
+    try:
+        inst.install()
+        import importlib
+        enc = importlib.import_module("models.Encoders")
+        net = importlib.import_module("models.Net")
+        assert enc.PostProcessModel().build() == (P.FeatureEncoderMult, P.FeatureiResnet)
+        assert net.FeatureEncoderMult is P.FeatureEncoderMult and net.FeatureEncoder is P.FeatureEncoder
+        assert net.Net.__module__ == "models.Net"                       # everything else untouched
+        inst.uninstall()
+        assert net.FeatureEncoderMult.__module__ == "models.Net" and enc.FeatureiResnet.__module__ == "models.Encoders"
+    finally:
+        inst.uninstall()
+        sys.path.remove(str(tmp_path))
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
 def test_conv_plans_for_every_generator_layer(lib):
     """Tiling decisions for the 17 StyledConvs of the 1024^2 generator (no device needed): shared memory
     fits the 227 KB opt-in limit, 4^2/8^2 use the per-tap kernel, everything else the halo kernel, the three

@@ -38,3 +38,29 @@ def test_fse_oracle_and_layout(golden_dir):
     assert lat.shape == (2, 18, 512) and content.shape == (2, 512, 16, 16)
     assert float((lat - torch.from_numpy(g["fse_latent"])).abs().max()) < 1e-4
     assert float((content[:, ::16] - torch.from_numpy(g["fse_content_sub"])).abs().max()) < 1e-4
+
+
+def test_postprocess_oracle_and_layout(golden_dir):
+    """PostProcess conv stack: FeatureEncoderMult(fs_layers=[9]) and FeatureiResnet."""
+    import hairfastgan_b200.postprocess as P
+    g = np.load(os.path.join(golden_dir, "postprocess.npz"))
+    enc = P.FeatureEncoderMult(fs_layers=[9], opts=None).eval()
+    params = EO.synth_params_like(enc, seed=31)
+    assert len(params) == int(g["mult_n_keys"])
+    enc.load_state_dict(params, strict=True)
+    x = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(32)) * 2 - 1
+    lat, (content,) = EO.feature_encoder_mult_ref(params, x)
+    assert lat.shape == (2, 18, 512) and content.shape == (2, 512, 64, 64)
+    assert float((lat - torch.from_numpy(g["mult_latent"])).abs().max()) < 1e-4
+    assert float((content[:, ::16, ::2, ::2] - torch.from_numpy(g["mult_content_sub"])).abs().max()) < 1e-4
+
+    fr = P.FeatureiResnet([[1024, 2], [768, 2], [512, 2]]).eval()
+    fparams = EO.synth_params_like(fr, seed=41)
+    assert len(fparams) == int(g["fres_n_keys"])
+    fr.load_state_dict(fparams, strict=True)
+    xf = torch.randn(2, 1024, 16, 16, generator=torch.Generator().manual_seed(42))
+    y = EO.feature_iresnet_ref(fparams, xf)
+    assert y.shape == (2, 512, 16, 16)
+    assert float((y[:, ::4] - torch.from_numpy(g["fres_out_sub"])).abs().max()) < 1e-4
+    with __import__("pytest").raises(NotImplementedError):
+        P.FeatureEncoderMult(fs_layers=[3], opts=None)          # 6x6 / stride-4 content conv: not on the path

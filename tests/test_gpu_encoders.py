@@ -117,3 +117,44 @@ def test_fse_encoder_golden(N, golden_dir):
     e2, rms2 = rel_err(content[:, ::16], torch.from_numpy(g["fse_content_sub"]))
     record("fse_encoder", latent_rel_max_err=e1, content_rel_max_err=e2, latent_rms=rms1, content_rms=rms2)
     assert e1 < TOL_ENC[dtype_name()] and e2 < TOL_ENC[dtype_name()], (e1, e2)
+
+
+def test_postprocess_feature_encoder_mult_golden(N, golden_dir):
+    """FeatureEncoderMult(fs_layers=[9]) (models/Net.py:396-477) vs the reference golden."""
+    import hairfastgan_b200.postprocess as P
+    g = np.load(os.path.join(golden_dir, "postprocess.npz"))
+    enc = P.FeatureEncoderMult(fs_layers=[9], opts=None).eval()
+    enc.load_state_dict(EO.synth_params_like(enc, seed=31), strict=True)
+    enc = enc.cuda()
+    x = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(32)) * 2 - 1
+    lat, content = enc(x.cuda())
+    assert isinstance(content, list) and len(content) == 1
+    assert lat.shape == (2, 18, 512) and content[0].shape == (2, 512, 64, 64)
+    e1, rms1 = rel_err(lat, torch.from_numpy(g["mult_latent"]))
+    e2, rms2 = rel_err(content[0][:, ::16, ::2, ::2], torch.from_numpy(g["mult_content_sub"]))
+    record("pp_feature_encoder_mult", latent_rel_max_err=e1, content_rel_max_err=e2, latent_rms=rms1, content_rms=rms2)
+    assert e1 < TOL_ENC[dtype_name()] and e2 < TOL_ENC[dtype_name()], (e1, e2)
+
+
+def test_postprocess_feature_iresnet(N, golden_dir):
+    """FeatureiResnet([[1024,2],[768,2],[512,2]]) (models/Encoders.py:35-57): reference golden on a
+    16x16 map, and the swap()-sized 64x64 map against the oracle through the size-independent structure."""
+    import hairfastgan_b200.postprocess as P
+    g = np.load(os.path.join(golden_dir, "postprocess.npz"))
+    fr = P.FeatureiResnet([[1024, 2], [768, 2], [512, 2]]).eval()
+    params = EO.synth_params_like(fr, seed=41)
+    fr.load_state_dict(params, strict=True)
+    fr = fr.cuda()
+    xf = torch.randn(2, 1024, 16, 16, generator=torch.Generator().manual_seed(42))
+    y = fr(xf.cuda())
+    assert y.shape == (2, 512, 16, 16)
+    e, rms = rel_err(y[:, ::4], torch.from_numpy(g["fres_out_sub"]))
+    record("pp_feature_iresnet_16", rel_max_err=e, ref_rms=rms)
+    assert e < TOL_ENC[dtype_name()], e
+    xl = torch.randn(1, 1024, 64, 64, generator=torch.Generator().manual_seed(43))
+    yl = fr(xl.cuda())
+    ref = EO.feature_iresnet_ref(params, xl)
+    e2, rms2 = rel_err(yl, ref)
+    record("pp_feature_iresnet_64", rel_max_err=e2, ref_rms=rms2)
+    assert yl.shape == (1, 512, 64, 64) and e2 < TOL_ENC[dtype_name()], e2
+    assert torch.equal(yl, fr(xl.cuda()))             # deterministic
