@@ -478,10 +478,14 @@ constexpr int kHaloPitch = kHaloTW + 2;   // dense halo rows (pitch 16 measured 
 constexpr int kMaxASlots = 8;
 constexpr int kMaxG = 8;
 
-template <int KCHUNK, int DT>
-__global__ void __launch_bounds__(kHaloThreads, 1)
+// NG = number of epilogue groups (4 warps each) = number of TMEM accumulator buffers of 512/NG columns.  NG = 4
+// (576 threads, <= 112 registers) serves the resident-weight low-channel layers, whose per-tile MMA time is shorter
+// than what two groups need for the epilogue (ncu: 2 epilogue warps per SM sub-partition issue 28 % of the time).
+template <int KCHUNK, int DT, int NG>
+__global__ void __launch_bounds__(64 + 128 * NG, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvKernelParams p) {
+  constexpr int BUF_COLS = 512 / NG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr uint32_t ROW_BYTES = KCHUNK * 2;
@@ -499,9 +503,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* b_empty = b_full + kMaxStages;          // [kMaxStages]
   uint64_t* a_full = b_empty + kMaxStages;          // [kMaxASlots]
   uint64_t* a_empty = a_full + kMaxASlots;          // [kMaxASlots]
-  uint64_t* tmem_full = a_empty + kMaxASlots;       // [2]
-  uint64_t* tmem_empty = tmem_full + 2;             // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* tmem_full = a_empty + kMaxASlots;       // [NG]
+  uint64_t* tmem_empty = tmem_full + 4;             // [NG]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -518,7 +522,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NG; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 128);
     }
@@ -590,11 +594,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int w = blockIdx.x; w < p.num_tiles; w += gridDim.x, ++it) {
       const int m0 = (w / p.num_n_tiles) * G;
       const int gcount = min(G, p.num_m_tiles - m0);
-      const int buf = it & 1;
-      const uint32_t use = (uint32_t)(it >> 1);
+      const int buf = it % NG;
+      const uint32_t use = (uint32_t)(it / NG);
       mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 256);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BUF_COLS);
       if (p.b_resident) {
         // order (tile g, tap): each halo slot is released as soon as its nine taps are issued
         for (int g = 0; g < gcount; ++g) {
@@ -656,19 +660,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     }  // elect_one
   } else {
-    // ================================ epilogue: two groups of 4 warps =============
-    const int grp = (warp - 2) >> 2;         // group g owns TMEM buffer g and the rounds with (it & 1) == g
+    // ================================ epilogue: NG groups of 4 warps ===============
+    const int grp = (warp - 2) >> 2;         // group g owns TMEM buffer g and the rounds with it % NG == g
     const int wq = warp & 3;
     const int row = wq * 32 + lane;
     const int etid = ((warp - 2) & 3) * 32 + lane;
     const int w_l = row & (kHaloTW - 1), h_l = row >> 3;
     const float nw = p.noise_w ? __ldg(p.noise_w) : 0.f;
-    TableEntry* my_table = table + grp * 256;
+    TableEntry* my_table = table + grp * BUF_COLS;
     int cached_bt = -1, cached_nt = -1;
     int it = 0;
     uint32_t use = 0;
     for (int w = blockIdx.x; w < p.num_tiles; w += gridDim.x, ++it) {
-      if ((it & 1) != grp) continue;
+      if ((it % NG) != grp) continue;
       const int nt = w % p.num_n_tiles, m0 = (w / p.num_n_tiles) * G;
       const int gcount = min(G, p.num_m_tiles - m0);
       const int n0 = nt * p.n_tile;
@@ -677,7 +681,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full[grp], use & 1);
       ++use;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * 256);
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * BUF_COLS);
       for (int g = 0; g < gcount; ++g) {
         const float4 nz = nz_next;
         const MTile cur = tc;
@@ -897,7 +901,7 @@ int conv_plan(const ConvLaunch& a, ConvPlan* p) {
   // the GEMM rows are OUTPUT pixels (input pixels for the polyphase up-conv)
   const int MH = stride == 2 ? (a.H + 1) / 2 : a.H, MW = stride == 2 ? (a.W + 1) / 2 : a.W;
   p->halo = (a.taps == 9 && stride == 1 && a.H % kHaloTH == 0 && a.W % kHaloTW == 0 && !env_int("HF_CONV_V1", 0)) ? 1 : 0;
-  p->G = 1; p->na_slots = 0; p->pitch = 0; p->b_resident = 0; p->a_slot_bytes = 0;
+  p->G = 1; p->na_slots = 0; p->pitch = 0; p->b_resident = 0; p->a_slot_bytes = 0; p->ng = 2;
   if (p->halo) {
     p->TW = kHaloTW; p->TH = kHaloTH; p->TB = 1;
   } else {
@@ -939,13 +943,6 @@ int conv_plan(const ConvLaunch& a, ConvPlan* p) {
   const size_t budget = 232448 - fixed;
   const int row_bytes = p->kchunk * 2;
   if (p->halo) {
-    // rounds: G tiles share one 256-column accumulator buffer; keep at least one round per SM
-    int G = 1;
-    const int gmax = env_int("HF_HALO_GMAX", kMaxG);
-    while (G * 2 <= gmax && G * 2 * n_tile <= 256 &&
-           (int64_t)(p->num_m_tiles / (G * 2)) * p->num_n_tiles >= sms)
-      G *= 2;
-    p->G = G;
     p->pitch = kHaloPitch;
     p->a_slot_bytes = (uint32_t)(((size_t)kHaloRows * p->pitch * row_bytes + 1023) & ~size_t(1023));
     const size_t tap_bytes = (size_t)n_tile * row_bytes;
@@ -953,6 +950,19 @@ int conv_plan(const ConvLaunch& a, ConvPlan* p) {
     p->b_resident = (kc == 1 && p->num_n_tiles == 1 && 9 * tap_bytes + 2 * (size_t)p->a_slot_bytes <= budget &&
                      env_int("HF_HALO_RESIDENT", 1))
                         ? 1 : 0;
+    // epilogue groups / accumulator buffers: the 32-channel resident-weight layers (18 MMAs per tile) are
+    // epilogue-bound with two groups and get four buffers of 128 columns and four groups.  Measured (B=4, us,
+    // NG=2 -> NG=4): 32->32@1024^2 220 -> 203, but 64->64@512^2 115 -> 125 and 64->32 up 154 -> 172 (smaller
+    // rounds, 96-register budget), so wider layers keep two groups.
+    p->ng = (p->b_resident && n_tile == 32 && env_int("HF_HALO_NG", 4) == 4) ? 4 : 2;
+    const int buf_cols = 512 / p->ng;
+    // rounds: G tiles share one accumulator buffer; keep at least one round per SM
+    int G = 1;
+    const int gmax = env_int("HF_HALO_GMAX", kMaxG);
+    while (G * 2 <= gmax && G * 2 * n_tile <= buf_cols &&
+           (int64_t)(p->num_m_tiles / (G * 2)) * p->num_n_tiles >= sms)
+      G *= 2;
+    p->G = G;
     if (p->b_resident) {
       int na = (int)((budget - 9 * tap_bytes) / p->a_slot_bytes);
       p->na_slots = na > kMaxASlots ? kMaxASlots : na;
@@ -1118,11 +1128,19 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st, ConvPlan* plan_out) {
     return bf ? launch_pair_kernel(conv_halo2_kernel<HF_BF16>, tmA, tmB, kp, pl, st)
               : launch_pair_kernel(conv_halo2_kernel<HF_F16>, tmA, tmB, kp, pl, st);
   if (pl.halo) {
+    constexpr int T4 = 64 + 128 * 4;
+    if (pl.ng == 4) {
+      if (pl.kchunk == 64)
+        return bf ? launch_kernel(conv_halo_kernel<64, HF_BF16, 4>, T4, tmA, tmB, kp, pl, st, "conv_halo")
+                  : launch_kernel(conv_halo_kernel<64, HF_F16, 4>, T4, tmA, tmB, kp, pl, st, "conv_halo");
+      return bf ? launch_kernel(conv_halo_kernel<32, HF_BF16, 4>, T4, tmA, tmB, kp, pl, st, "conv_halo")
+                : launch_kernel(conv_halo_kernel<32, HF_F16, 4>, T4, tmA, tmB, kp, pl, st, "conv_halo");
+    }
     if (pl.kchunk == 64)
-      return bf ? launch_kernel(conv_halo_kernel<64, HF_BF16>, kHaloThreads, tmA, tmB, kp, pl, st, "conv_halo")
-                : launch_kernel(conv_halo_kernel<64, HF_F16>, kHaloThreads, tmA, tmB, kp, pl, st, "conv_halo");
-    return bf ? launch_kernel(conv_halo_kernel<32, HF_BF16>, kHaloThreads, tmA, tmB, kp, pl, st, "conv_halo")
-              : launch_kernel(conv_halo_kernel<32, HF_F16>, kHaloThreads, tmA, tmB, kp, pl, st, "conv_halo");
+      return bf ? launch_kernel(conv_halo_kernel<64, HF_BF16, 2>, kHaloThreads, tmA, tmB, kp, pl, st, "conv_halo")
+                : launch_kernel(conv_halo_kernel<64, HF_F16, 2>, kHaloThreads, tmA, tmB, kp, pl, st, "conv_halo");
+    return bf ? launch_kernel(conv_halo_kernel<32, HF_BF16, 2>, kHaloThreads, tmA, tmB, kp, pl, st, "conv_halo")
+              : launch_kernel(conv_halo_kernel<32, HF_F16, 2>, kHaloThreads, tmA, tmB, kp, pl, st, "conv_halo");
   }
   if (pl.kchunk == 64)
     return bf ? launch_kernel(conv_igemm_kernel<64, HF_BF16>, kConvThreads, tmA, tmB, kp, pl, st, "conv_igemm")

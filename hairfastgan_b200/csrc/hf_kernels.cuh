@@ -109,6 +109,7 @@ struct ConvLaunch {
 struct ConvPlan {
   int halo;               // 1: conv_halo_kernel (halo tile in smem, shifted descriptors); 0: conv_igemm_kernel
   int G;                  // halo: tiles per round (share one accumulator buffer and each weight tile)
+  int ng;                 // halo: epilogue groups = TMEM accumulator buffers (2 x 256 or 4 x 128 columns)
   int na_slots, pitch;    // halo: ring slots, halo row pitch in pixels
   int b_resident;         // halo: whole weight matrix stays in smem
   uint32_t a_slot_bytes;

@@ -179,5 +179,5 @@ def test_conv_plans_for_every_generator_layer(lib):
                 assert na >= max(2, G) and pitch in (10, 16)
             if halo == 2:      # CTA-pair kernel: full 256-wide N tile, one tile per CTA
                 assert n_tile == 256 and G == 1 and res == 0 and grid % 2 == 0
-            if batch == 4 and i in (14, 15, 16):
-                assert res == 1 and G == {14: 4, 15: 2, 16: 8}[i]
+            if batch == 4 and i in (14, 15, 16):   # resident weights; layer 16 runs four 128-column accumulator buffers
+                assert res == 1 and G == {14: 4, 15: 2, 16: 4}[i]
