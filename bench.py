@@ -124,7 +124,10 @@ def run_ours(args, rank, world, local_rank):
             prm.data.normal_(0, 0.1)
     # the dominant kernel is timed ALONE and first (burst peak in the denominator): later in the run the board sits at
     # its power cap (nvidia-smi: sw_power_cap, ~1.76 GHz) and the same launch measures ~15 % lower
-    roofline = time_dominant_kernel(gen, dev) if (rank == 0 and world == 1) else None
+    roofline = roofline_b4 = None
+    if rank == 0 and world == 1:
+        roofline_b4 = time_dominant_kernel(gen, dev, 4)
+        roofline = time_dominant_kernel(gen, dev, 3 * args.triples)      # the batch the step's full forwards use
     e4e = E.Encoder4Editing(50, "ir_se", types.SimpleNamespace(stylegan_size=1024)).to(dev).eval()
     fse = E.fs_encoder_v2(n_styles=18, opts=None, stride=(2, 2)).to(dev).eval()
     import hairfastgan_b200.postprocess as PP
@@ -251,6 +254,7 @@ def run_ours(args, rank, world, local_rank):
                                     "feature_iresnet_ms": round(ms_ppr, 3)}
         del xr
         extra["roofline"] = roofline
+        extra["roofline_b4"] = roofline_b4
     if world > 1:
         dist.destroy_process_group()
     h2d = sum(t.numel() * 4 for t in host_lat) + sum(t.numel() * 4 for t in host_lin if t is not None) \
@@ -258,16 +262,16 @@ def run_ours(args, rank, world, local_rank):
     return ms, ms_e2e, n_launch, clocks, extra, h2d
 
 
-def time_dominant_kernel(gen, dev):
-    """The 512->512 3x3 @64^2 convolution (BASELINE configs[0] shape) at B=4: the layer class that carries most of
-    the tensor-core time.  Algorithmic FLOPs = 2*512*512*9*64^2 per sample."""
+def time_dominant_kernel(gen, dev, B=4):
+    """The 512->512 3x3 @64^2 convolution (BASELINE configs[0] shape), the layer class that carries most of the
+    tensor-core time, at batch B (the step runs it at B = 3T and T; configs[1] is B = 4).  Algorithmic FLOPs =
+    2*512*512*9*64^2 per sample."""
     import ctypes as C
     import torch
     from hairfastgan_b200 import _lib
     import hairfastgan_b200.model as M
     lib = _lib.lib()
     conv = gen.convs[7].conv                       # convs.7 = 512->512 @64^2
-    B = 4
     desc, blob = conv._packed.get(conv, M.default_dtype())
     x = torch.randn(B, 512, 64, 64, device=dev); st = torch.randn(B, 512, device=dev)
     y = torch.empty(B, 512, 64, 64, device=dev)
@@ -288,10 +292,10 @@ def time_dominant_kernel(gen, dev):
     achieved = flops / (ms.value * 1e-3) / 1e12
     pk = peaks()
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_dominant_kernel_r1.json")
+    tp = os.path.join(ROOT, "profiles", "ncu_dominant_kernel_r1.json" if B == 4 else f"ncu_dominant_kernel_r1_b{B}.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    return {"kernel": f"{kname}<bf16> 512->512 3x3 @64^2 B=4 (+fp32 NCHW store)", "bound": "tensor",
+    return {"kernel": f"{kname}<bf16> 512->512 3x3 @64^2 B={B} (+fp32 NCHW store)", "bound": "tensor",
             "achieved": round(achieved, 1), "peak": pk["tf_burst"], "unit": "TFLOP/s",
             "frac": round(achieved / pk["tf_burst"], 4), "peak_source": pk["src"] + " burst (kernel timed alone)",
             "launch_ms": round(ms.value, 4), "traffic": traffic}

@@ -256,6 +256,36 @@ __global__ void __launch_bounds__(256) affine_kernel(const __grid_constant__ Aff
   if (i >= job.C) return;
   const float* wrow = job.mw + (size_t)i * D;
   const float mb = __ldg(job.mb + i);
+  if (D == 512) {
+    // the usual case (style_dim 512): the weight row lives in registers, four samples in flight per pass
+    float4 w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = __ldg(reinterpret_cast<const float4*>(wrow + lane * 4 + q * 128));
+    for (int b0 = 0; b0 < B; b0 += 4) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int b = min(b0 + u, B - 1);
+        const float* srow = job.style + (size_t)b * style_stride;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 s = __ldg(reinterpret_cast<const float4*>(srow + lane * 4 + q * 128));
+          acc[u] = fmaf(w[q].x, s.x, acc[u]); acc[u] = fmaf(w[q].y, s.y, acc[u]);
+          acc[u] = fmaf(w[q].z, s.z, acc[u]); acc[u] = fmaf(w[q].w, s.w, acc[u]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+      }
+      if (lane < 4 && b0 + lane < B) {
+        const float a = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+        job.s[(size_t)(b0 + lane) * job.C + i] = fmaf(a, job.wscale, mb);
+      }
+    }
+    return;
+  }
   for (int b = 0; b < B; ++b) {
     const float* srow = job.style + (size_t)b * style_stride;
     float acc = 0.f;
@@ -278,6 +308,36 @@ __global__ void __launch_bounds__(256) demod_kernel(const __grid_constant__ Demo
   const int o = ((int)blockIdx.x - job.block_begin) * 8 + warp;
   if (o >= job.Cout) return;
   const float* wrow = job.wsq + (size_t)o * job.Cin;
+  if (job.Cin <= 512) {
+    // Wsq row in registers (<= 16 values per lane), four samples in flight per pass; same summation order as below
+    float w[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) w[q] = (lane + 32 * q < job.Cin) ? __ldg(wrow + lane + 32 * q) : 0.f;
+    for (int b0 = 0; b0 < B; b0 += 4) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* srow = job.s + (size_t)min(b0 + u, B - 1) * job.Cin;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          if (lane + 32 * q < job.Cin) {
+            const float s = __ldg(srow + lane + 32 * q);
+            acc[u] = fmaf(s * s, w[q], acc[u]);
+          }
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], off);
+      }
+      if (lane < 4 && b0 + lane < B) {
+        const float a = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+        job.d[(size_t)(b0 + lane) * job.Cout + o] = rsqrtf(a + 1e-8f);
+      }
+    }
+    return;
+  }
   for (int b = 0; b < B; ++b) {
     const float* srow = job.s + (size_t)b * job.Cin;
     float acc = 0.f;
