@@ -41,7 +41,8 @@ class hf_conv2d_io(C.Structure):
     _fields_ = [("batch", C.c_int), ("height", C.c_int), ("width", C.c_int), ("x16", C.c_void_p),
                 ("shift", C.c_void_p), ("act", C.c_int), ("slope", C.c_void_p), ("slope0", C.c_float),
                 ("residual16", C.c_void_p), ("y16", C.c_void_p), ("y16b_scale", C.c_void_p),
-                ("y16b_shift", C.c_void_p), ("y16b", C.c_void_p), ("y32_nchw", C.c_void_p)]
+                ("y16b_shift", C.c_void_p), ("y16b", C.c_void_p), ("y32_nchw", C.c_void_p),
+                ("act_after_residual", C.c_int)]
 
 
 class hf_gen_config(C.Structure):
@@ -111,6 +112,16 @@ SYMBOLS = {
                                          C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hf_adaptive_avgpool_nhwc16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                              C.c_int, C.c_int, C.c_void_p]),
+    "hf_stem7x7s2_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_void_p]),
+    "hf_maxpool3x3s2_nhwc16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p]),
+    "hf_pooled_fc_nhwc16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hf_gate_add_up_nhwc16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hf_bilinear_upsample_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.c_int, C.c_int, C.c_void_p]),
     "hf_generator_packed_bytes": (C.c_size_t, [C.POINTER(hf_gen_config)]),
     "hf_generator_workspace_bytes": (C.c_size_t, [C.POINTER(hf_gen_config), C.c_int]),
     "hf_generator_pack": (C.c_int, [C.POINTER(hf_gen_config), C.POINTER(hf_gen_weights), C.c_void_p, C.c_void_p]),

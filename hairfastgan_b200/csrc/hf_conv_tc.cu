@@ -67,7 +67,7 @@ struct ConvKernelParams {
   // plain (encoder) convolution: epi == 1 -> v = act(acc*scale[o] + shift[o]) + residual;
   // y16 (= xhat_out) = v ; y16b = v*s2[o] + b2[o] ; out_nchw = v
   int dbg;
-  int epi, stride, cin_g, cout_g, enc_act;
+  int epi, stride, cin_g, cout_g, enc_act, enc_post;
   float enc_slope0;
   const float* enc_scale;
   const float* enc_shift;
@@ -160,7 +160,7 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
 // / 0 (ReLU) / per-channel (PReLU) / constant (LeakyReLU), so there is no per-element branch.
 template <int DT, bool RES, bool Y16B, bool NCHW>
 __device__ __forceinline__ void epi_chunk_enc(uint32_t ts, const uint32_t (&acc)[32], const uint4* res, uint4* dst,
-                                              uint4* dst_b, float* onchw, size_t plane_o) {
+                                              uint4* dst_b, float* onchw, size_t plane_o, bool post) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     uint32_t rw[4] = {0u, 0u, 0u, 0u};
@@ -179,8 +179,18 @@ __device__ __forceinline__ void epi_chunk_enc(uint32_t ts, const uint32_t (&acc)
         const int j = g * 8 + h * 2 + u;
         const float4 ta = lds128(ts + (uint32_t)j * 32u);
         float a = fmaf(__uint_as_float(acc[j]), ta.x, ta.y);
-        a = fmaf(fminf(a, 0.f), ta.z, fmaxf(a, 0.f));
-        if (RES) a += Half2T<DT>::to_float((uint16_t)(u ? (rw[h] >> 16) : (rw[h] & 0xFFFFu)));
+        if (RES) {
+          const float r = Half2T<DT>::to_float((uint16_t)(u ? (rw[h] >> 16) : (rw[h] & 0xFFFFu)));
+          if (post) {                      // ResNet BasicBlock: activation after the residual add (CTA-uniform)
+            a += r;
+            a = fmaf(fminf(a, 0.f), ta.z, fmaxf(a, 0.f));
+          } else {
+            a = fmaf(fminf(a, 0.f), ta.z, fmaxf(a, 0.f));
+            a += r;
+          }
+        } else {
+          a = fmaf(fminf(a, 0.f), ta.z, fmaxf(a, 0.f));
+        }
         if (NCHW) { if (onchw) onchw[(size_t)j * plane_o] = a; }
         v[u] = a;
         if (Y16B) {
@@ -208,6 +218,7 @@ __device__ __forceinline__ void epilogue_tile_enc(const ConvKernelParams& p, con
   const size_t pix = valid ? ((size_t)b * p.Ho + y) * p.Wo + x : 0;
   const uint32_t trow_s = smem_u32(trow);
   const int variant = p.out_nchw ? 3 : ((p.enc_residual ? 1 : 0) | (p.enc_y16b ? 2 : 0));
+  const bool post = p.enc_post != 0;
   for (int q = 0; q < chunks; ++q) {
     uint32_t acc[32];
     tmem_ld_32x32(taddr + q * 32, acc);
@@ -225,10 +236,10 @@ __device__ __forceinline__ void epilogue_tile_enc(const ConvKernelParams& p, con
                                          : nullptr;
     const uint32_t ts = trow_s + (uint32_t)(q * 32) * (uint32_t)sizeof(TableEntry);
     switch (variant) {       // uniform across the CTA
-      case 0: epi_chunk_enc<DT, false, false, false>(ts, acc, res, dst, dst_b, onchw, plane_o); break;
-      case 1: epi_chunk_enc<DT, true, false, false>(ts, acc, res, dst, dst_b, onchw, plane_o); break;
-      case 2: epi_chunk_enc<DT, false, true, false>(ts, acc, res, dst, dst_b, onchw, plane_o); break;
-      default: epi_chunk_enc<DT, true, true, true>(ts, acc, res, dst, dst_b, onchw, plane_o); break;
+      case 0: epi_chunk_enc<DT, false, false, false>(ts, acc, res, dst, dst_b, onchw, plane_o, post); break;
+      case 1: epi_chunk_enc<DT, true, false, false>(ts, acc, res, dst, dst_b, onchw, plane_o, post); break;
+      case 2: epi_chunk_enc<DT, false, true, false>(ts, acc, res, dst, dst_b, onchw, plane_o, post); break;
+      default: epi_chunk_enc<DT, true, true, true>(ts, acc, res, dst, dst_b, onchw, plane_o, post); break;
     }
   }
 }
@@ -1113,7 +1124,7 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st, ConvPlan* plan_out) {
   kp.rgb_s = a.rgb_s;
   kp.rgb_partial = a.rgb_partial;
   kp.dbg = env_int("HF_CONV_DBG", 0);       // experiments only: 1 = epilogue reduced to the TMEM read + release
-  kp.epi = a.epi; kp.stride = stride; kp.cin_g = cin_g;
+  kp.epi = a.epi; kp.stride = stride; kp.cin_g = cin_g; kp.enc_post = a.enc_post;
   kp.cout_g = (a.up ? 4 * a.Cout : a.Cout) / groups;
   kp.enc_act = a.enc_act; kp.enc_slope0 = a.enc_slope0;
   kp.enc_scale = a.enc_scale; kp.enc_shift = a.enc_shift; kp.enc_slope = a.enc_slope;

@@ -57,6 +57,7 @@ int hf_conv2d_forward(const hf_conv2d_desc* d, const void* packed, const hf_conv
   cl.enc_shift = io->shift; cl.enc_act = io->act; cl.enc_slope = io->act == 1 ? io->slope : nullptr;
   cl.enc_slope0 = io->slope0;
   cl.enc_residual = io->residual16;
+  cl.enc_post = io->act_after_residual ? 1 : 0;
   cl.xhat_out = io->y16;
   cl.enc_s2 = io->y16b_scale; cl.enc_b2 = io->y16b_shift; cl.enc_y16b = io->y16b;
   cl.out_nchw = io->y32_nchw;
@@ -121,6 +122,45 @@ int hf_adaptive_avgpool_nhwc16(const void* x16, float* y, int batch, int height,
   int rc = ensure_device_current();
   if (rc) return rc;
   return launch_adaptive_avgpool(x16, y, batch, height, width, channels, oh, ow, dtype, (cudaStream_t)stream);
+}
+
+/* ---- BiSeNet glue ---- */
+int hf_stem7x7s2_forward(const float* x, const float* weight_t, const float* shift, void* y16, int batch, int height,
+                         int width, int dtype, void* stream) {
+  int rc = ensure_device_current();
+  if (rc) return rc;
+  return launch_stem7x7(x, weight_t, shift, y16, batch, height, width, dtype, (cudaStream_t)stream);
+}
+
+int hf_maxpool3x3s2_nhwc16(const void* x16, void* y16, int batch, int height, int width, int channels, int dtype,
+                           void* stream) {
+  int rc = ensure_device_current();
+  if (rc) return rc;
+  return launch_maxpool3x3s2(x16, y16, batch, height, width, channels, dtype, (cudaStream_t)stream);
+}
+
+int hf_pooled_fc_nhwc16(const void* x16, const float* weight, const float* scale, const float* shift, int act,
+                        float* out, void* workspace, int batch, int hw, int channels, int cout, int dtype,
+                        void* stream) {
+  int rc = ensure_device_current();
+  if (rc) return rc;
+  return launch_pooled_fc(x16, weight, scale, shift, act, out, (float*)workspace, batch, hw, channels, cout, dtype,
+                          (cudaStream_t)stream);
+}
+
+int hf_gate_add_up_nhwc16(const void* x16, const float* gate, const float* addvec, const void* addt16, void* y16,
+                          int batch, int height, int width, int channels, int up, int dtype, void* stream) {
+  int rc = ensure_device_current();
+  if (rc) return rc;
+  return launch_gate_add_up(x16, gate, addvec, addt16, y16, batch, height, width, channels, up, dtype,
+                            (cudaStream_t)stream);
+}
+
+int hf_bilinear_upsample_nchw_f32(const float* x, float* y, int batch, int channels, int in_channels, int h, int w,
+                                  int height, int width, void* stream) {
+  int rc = ensure_device_current();
+  if (rc) return rc;
+  return launch_bilinear_up_nchw(x, y, batch, channels, in_channels, h, w, height, width, (cudaStream_t)stream);
 }
 
 }  // extern "C"

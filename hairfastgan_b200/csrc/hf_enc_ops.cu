@@ -198,6 +198,19 @@ int launch_se_gate(const void* x16, const float* fc1, const float* fc2, float* o
   HF_REQUIRE(x16 && out && ws, "se_gate: null pointer");
   HF_REQUIRE(C % 8 == 0 && B > 0 && HW > 0, "se_gate: channels must be a multiple of 8");
   HF_REQUIRE((fc1 == nullptr) == (fc2 == nullptr) && (!fc1 || (Cr > 0 && Cr <= 4096)), "se_gate: bad fc weights");
+  int S = 1;
+  const int rc = launch_channel_partial(x16, ws, B, HW, C, dtype, st, &S);
+  if (rc) return rc;
+  se_gate_kernel<<<B, 256, (size_t)(C + (fc1 ? Cr : 0)) * sizeof(float), st>>>(ws, S, 1.f / (float)HW, fc1, fc2, out, C,
+                                                                                 Cr);
+  HF_LAUNCH_OK("se_gate");
+  count_launch();
+  return HF_OK;
+}
+
+// stage 1 alone: ws[(b*S + s)*C + c] = partial channel sums; *splits = S
+int launch_channel_partial(const void* x16, float* ws, int B, int HW, int C, int dtype, cudaStream_t st, int* splits) {
+  HF_REQUIRE(x16 && ws && C % 8 == 0 && B > 0 && HW > 0, "channel_partial: bad arguments");
   const int S = channel_reduce_splits(B, HW, C), chunk = cdiv_i(HW, S);
   dim3 grid(cdiv_i(C, 64), B, S);
   if (dtype == HF_BF16)
@@ -205,10 +218,8 @@ int launch_se_gate(const void* x16, const float* fc1, const float* fc2, float* o
   else
     channel_sum_partial_kernel<HF_F16><<<grid, 256, 0, st>>>((const uint16_t*)x16, ws, HW, C, chunk);
   HF_LAUNCH_OK("channel_sum_partial");
-  se_gate_kernel<<<B, 256, (size_t)(C + (fc1 ? Cr : 0)) * sizeof(float), st>>>(ws, S, 1.f / (float)HW, fc1, fc2, out, C,
-                                                                                 Cr);
-  HF_LAUNCH_OK("se_gate");
-  count_launch(2);
+  count_launch();
+  if (splits) *splits = S;
   return HF_OK;
 }
 

@@ -59,6 +59,17 @@ int launch_nchw_to_nhwc16(const float* x, const float* scale, const float* shift
                           int HW, int dtype, cudaStream_t st);
 int launch_nhwc16_to_nchw(const void* x16, float* y, int B, int C, int HW, int dtype, cudaStream_t st);
 int channel_reduce_splits(int B, int HW, int C);
+int launch_channel_partial(const void* x16, float* ws, int B, int HW, int C, int dtype, cudaStream_t st, int* splits);
+// BiSeNet glue (hf_seg_ops.cu)
+int launch_stem7x7(const float* x, const float* w, const float* shift, void* y16, int B, int H, int W, int dtype,
+                   cudaStream_t st);
+int launch_maxpool3x3s2(const void* x16, void* y16, int B, int H, int W, int C, int dtype, cudaStream_t st);
+int launch_pooled_fc(const void* x16, const float* w, const float* scale, const float* shift, int act, float* out,
+                     float* ws, int B, int HW, int C, int Cout, int dtype, cudaStream_t st);
+int launch_gate_add_up(const void* x16, const float* gate, const float* addvec, const void* addt16, void* y16, int B,
+                       int h, int w, int C, int up, int dtype, cudaStream_t st);
+int launch_bilinear_up_nchw(const float* x, float* y, int B, int C, int Cin, int h, int w, int H, int W,
+                            cudaStream_t st);
 int launch_se_gate(const void* x16, const float* fc1, const float* fc2, float* out, float* ws, int B, int HW, int C,
                    int Cr, int dtype, cudaStream_t st);
 int launch_scale_add(const void* res16, const float* se, const void* shortcut16, int sc_stride, const float* s2,
@@ -99,6 +110,7 @@ struct ConvLaunch {
   const float* enc_scale; // [Cout] accumulator scale (NULL = 1)
   const float* enc_shift; // [Cout] bias / BN shift (NULL = 0)
   int enc_act;            // 0 none, 1 PReLU(enc_slope[Cout]), 2 LeakyReLU(enc_slope0), 3 ReLU
+  int enc_post;           // 1: the activation follows the residual add
   const float* enc_slope;
   float enc_slope0;
   const void* enc_residual;   // [B,Ho,Wo,Cout] 16-bit NHWC added after the activation, or NULL

@@ -78,7 +78,7 @@ class PackedConv2d:
         self.cout, self.k, self.stride, self.dtype = cout, k, stride, dt
 
     def __call__(self, x16: torch.Tensor, shift=None, act: int = 0, slope=None, slope0: float = 0.0, residual16=None,
-                 want_y16: bool = True, y16b_affine=None, want_y32: bool = False):
+                 want_y16: bool = True, y16b_affine=None, want_y32: bool = False, act_after_residual: bool = False):
         """Returns (y16 | None, y16b | None, y32 | None)."""
         b, h, w, _ = x16.shape
         ho, wo = ((h + 1) // 2, (w + 1) // 2) if self.stride == 2 else (h, w)
@@ -89,6 +89,7 @@ class PackedConv2d:
         io.shift, io.act, io.slope, io.slope0 = _p(keep[0]), act, _p(keep[1]), float(slope0)
         if residual16 is not None:
             io.residual16 = residual16.data_ptr()
+        io.act_after_residual = 1 if act_after_residual else 0
         y16 = y16b = y32 = None
         if want_y16:
             y16 = torch.empty(b, ho, wo, self.cout, device=dev, dtype=torch_dtype(self.dtype))
@@ -160,4 +161,66 @@ def adaptive_avgpool(x16, oh: int, ow: int, dtype: Optional[int] = None):
     y = torch.empty(b, c, oh, ow, device=x16.device, dtype=torch.float32)
     _lib.check(_lib.lib().hf_adaptive_avgpool_nhwc16(x16.data_ptr(), y.data_ptr(), b, h, w, c, oh, ow, dt,
                                                      _lib.stream_ptr()), "hf_adaptive_avgpool_nhwc16")
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ BiSeNet glue
+def stem7x7s2(x: torch.Tensor, weight: torch.Tensor, bn: torch.nn.BatchNorm2d, dtype: Optional[int] = None):
+    """Resnet18.conv1 + bn1 + ReLU (face_parsing/resnet.py:60-61,69-70): [B,3,H,W] fp32 -> [B,Ho,Wo,64] 16-bit NHWC."""
+    if not x.is_cuda:
+        raise RuntimeError("stem7x7s2: input must be a CUDA tensor (no CPU fallback)")
+    dt = default_dtype() if dtype is None else dtype
+    scale, shift = bn_affine(bn)
+    wt = (_f32(weight) * scale.view(-1, 1, 1, 1)).reshape(64, 147).t().contiguous()       # [147][64], BN scale folded
+    xf = _f32(x)
+    b, _, h, w = xf.shape
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    y = torch.empty(b, ho, wo, 64, device=x.device, dtype=torch_dtype(dt))
+    _lib.use_device(x.device.index)
+    _lib.check(_lib.lib().hf_stem7x7s2_forward(xf.data_ptr(), wt.data_ptr(), shift.data_ptr(), y.data_ptr(), b, h, w, dt,
+                                               _lib.stream_ptr()), "hf_stem7x7s2_forward")
+    return y
+
+
+def maxpool3x3s2(x16: torch.Tensor, dtype: Optional[int] = None):
+    dt = default_dtype() if dtype is None else dtype
+    b, h, w, c = x16.shape
+    y = torch.empty(b, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c, device=x16.device, dtype=x16.dtype)
+    _lib.check(_lib.lib().hf_maxpool3x3s2_nhwc16(x16.data_ptr(), y.data_ptr(), b, h, w, c, dt, _lib.stream_ptr()),
+               "hf_maxpool3x3s2_nhwc16")
+    return y
+
+
+def pooled_fc(x16: torch.Tensor, weight: torch.Tensor, scale=None, shift=None, act: int = 0,
+              dtype: Optional[int] = None):
+    """act((W . mean_hw(x)) * scale + shift): [B,H,W,C] 16-bit NHWC -> [B,Cout] fp32 (act: 0 none, 1 ReLU, 2 sigmoid)."""
+    dt = default_dtype() if dtype is None else dtype
+    b, h, w, c = x16.shape
+    wf = _f32(weight).reshape(weight.shape[0], c)
+    sc, sh = _f32(scale), _f32(shift)
+    out = torch.empty(b, wf.shape[0], device=x16.device, dtype=torch.float32)
+    ws = torch.empty(_lib.lib().hf_channel_reduce_workspace_bytes(b, h * w, c), device=x16.device, dtype=torch.uint8)
+    _lib.check(_lib.lib().hf_pooled_fc_nhwc16(x16.data_ptr(), wf.data_ptr(), _p(sc), _p(sh), act, out.data_ptr(),
+                                              ws.data_ptr(), b, h * w, c, wf.shape[0], dt, _lib.stream_ptr()),
+               "hf_pooled_fc_nhwc16")
+    return out
+
+
+def gate_add_up(x16: torch.Tensor, gate=None, addvec=None, addt16=None, up: int = 1, dtype: Optional[int] = None):
+    """nearest_up(x * gate[b,c] + addvec[b,c] + addt): [B,h,w,C] -> [B,h*up,w*up,C] 16-bit NHWC."""
+    dt = default_dtype() if dtype is None else dtype
+    b, h, w, c = x16.shape
+    y = torch.empty(b, h * up, w * up, c, device=x16.device, dtype=x16.dtype)
+    g, a = _f32(gate), _f32(addvec)
+    _lib.check(_lib.lib().hf_gate_add_up_nhwc16(x16.data_ptr(), _p(g), _p(a), _p(addt16), y.data_ptr(), b, h, w, c, up, dt,
+                                                _lib.stream_ptr()), "hf_gate_add_up_nhwc16")
+    return y
+
+
+def bilinear_upsample_nchw(x: torch.Tensor, channels: int, height: int, width: int):
+    """F.interpolate(x[:, :channels], (height, width), mode='bilinear', align_corners=True) on fp32 NCHW."""
+    b, cin, h, w = x.shape
+    y = torch.empty(b, channels, height, width, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hf_bilinear_upsample_nchw_f32(x.data_ptr(), y.data_ptr(), b, channels, cin, h, w, height, width,
+                                                        _lib.stream_ptr()), "hf_bilinear_upsample_nchw_f32")
     return y

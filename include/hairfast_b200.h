@@ -224,6 +224,8 @@ typedef struct {
   const float* y16b_shift;  /*   conv (cannot be folded into its weights because of the zero padding)          */
   void* y16b;
   float* y32_nchw;          /* [B,cout,Ho,Wo] fp32 NCHW or NULL */
+  int act_after_residual;   /* 0: v = act(conv) + residual (IR blocks); 1: v = act(conv + residual) (ResNet BasicBlock,
+                               face_parsing/resnet.py:44-46) */
 } hf_conv2d_io;
 
 /* Replaces nn.Conv2d.forward (+ the folded BatchNorm2d / PReLU / LeakyReLU / residual add around it). */
@@ -255,6 +257,31 @@ int hf_upsample_add_nhwc16(const void* x16, const void* y16, void* out16, int ba
 /* nn.AdaptiveAvgPool2d((oh,ow)) -> fp32 NCHW [B,C,oh,ow] */
 int hf_adaptive_avgpool_nhwc16(const void* x16, float* y, int batch, int height, int width, int channels, int oh,
                                int ow, int dtype, void* stream);
+
+/* ---- BiSeNet face parsing (models/CtrlHair/external_code/face_parsing/{model,resnet}.py) ---- */
+/* Resnet18.conv1 + bn1 + ReLU (resnet.py:60-61,69-70): 7x7 / stride 2 / pad 3, 3 -> 64 channels.
+ * x [B,3,H,W] fp32 NCHW; weight_t [147][64] fp32 = conv weight [64,3,7,7] transposed to (c,ky,kx)-major with the
+ * BatchNorm scale folded in; shift [64]; y16 [B,Ho,Wo,64] 16-bit NHWC, Ho = (H-1)/2+1. */
+int hf_stem7x7s2_forward(const float* x, const float* weight_t, const float* shift, void* y16, int batch, int height,
+                         int width, int dtype, void* stream);
+/* nn.MaxPool2d(3, 2, 1) (resnet.py:62,71) on 16-bit NHWC; output (H-1)/2+1 x (W-1)/2+1 */
+int hf_maxpool3x3s2_nhwc16(const void* x16, void* y16, int batch, int height, int width, int channels, int dtype,
+                           void* stream);
+/* 1x1 conv of the globally pooled feature + folded BatchNorm + activation (act: 0 none, 1 ReLU, 2 sigmoid):
+ * out[b,o] = act((sum_c weight[o,c] * mean_hw(x)[b,c]) * scale[o] + shift[o]); scale / shift may be NULL.
+ * AttentionRefinementModule attention (model.py:82-86), ContextPath.conv_avg (model.py:114-115).
+ * workspace: hf_channel_reduce_workspace_bytes(batch, hw, channels). */
+int hf_pooled_fc_nhwc16(const void* x16, const float* weight, const float* scale, const float* shift, int act,
+                        float* out, void* workspace, int batch, int hw, int channels, int cout, int dtype,
+                        void* stream);
+/* ContextPath merge (model.py:116-128): y[b,Y,X,c] = x[b,Y/up,X/up,c]*gate[b,c] + addvec[b,c] + addt[b,Y/up,X/up,c];
+ * up = 1 or 2 (F.interpolate nearest); gate / addvec / addt16 may be NULL; height, width = input size. */
+int hf_gate_add_up_nhwc16(const void* x16, const float* gate, const float* addvec, const void* addt16, void* y16,
+                          int batch, int height, int width, int channels, int up, int dtype, void* stream);
+/* F.interpolate(bilinear, align_corners=True) (model.py:239-241) of the first `channels` of `in_channels` planes:
+ * x [B,in_channels,h,w] -> y [B,channels,height,width], fp32 NCHW */
+int hf_bilinear_upsample_nchw_f32(const float* x, float* y, int batch, int channels, int in_channels, int h, int w,
+                                  int height, int width, void* stream);
 
 /* Number of kernels the last hf_generator_forward / hf_conv_forward of this thread launched. */
 int hf_last_launch_count(void);

@@ -114,6 +114,8 @@ def test_install_overlay_redirects_reference_imports():
         assert fse.Generator.__module__ == "hairfastgan_b200.fse_model" and callable(fse.get_keys)
         psp = importlib.import_module("models.encoder4editing.models.encoders.psp_encoders")
         assert psp.Encoder4Editing.__module__ == "hairfastgan_b200.encoders"
+        seg = importlib.import_module("models.CtrlHair.external_code.face_parsing.model")     # my_parsing_util.py:15
+        assert seg.BiSeNet.__module__ == "hairfastgan_b200.bisenet"
         ns = {}
         exec("from nets.feature_style_encoder import *", ns)          # trainer.py:20
         assert ns["fs_encoder_v2"].__module__ == "hairfastgan_b200.encoders"

@@ -40,6 +40,25 @@ def test_fse_oracle_and_layout(golden_dir):
     assert float((content[:, ::16] - torch.from_numpy(g["fse_content_sub"])).abs().max()) < 1e-4
 
 
+def test_bisenet_oracle_and_layout(golden_dir):
+    """BiSeNet: oracle vs the reference golden, state_dict layout of the drop-in module."""
+    import hairfastgan_b200.bisenet as B
+    from oracle import bisenet_oracle as BO
+    g = np.load(os.path.join(golden_dir, "bisenet.npz"))
+    net = B.BiSeNet(n_classes=19).eval()
+    params = EO.synth_params_like(net, seed=51)
+    assert len(params) == int(g["n_keys"])
+    net.load_state_dict(params, strict=True)
+    x = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(52)) * 2 - 1
+    out, out16, out32 = BO.bisenet_ref(params, x)
+    assert out.shape == (2, 19, 256, 256)
+    assert float((out[:, :, ::4, ::4] - torch.from_numpy(g["out_sub"])).abs().max()) < 2e-4
+    assert float((out16[:, :, ::8, ::8] - torch.from_numpy(g["out16_sub"])).abs().max()) < 2e-4
+    assert float((out32[:, :, ::8, ::8] - torch.from_numpy(g["out32_sub"])).abs().max()) < 2e-4
+    low = BO.bisenet_ref(params, x, return_lowres=True)
+    assert float((low[0] - torch.from_numpy(g["low_out"])).abs().max()) < 2e-4
+
+
 def test_postprocess_oracle_and_layout(golden_dir):
     """PostProcess conv stack: FeatureEncoderMult(fs_layers=[9]) and FeatureiResnet."""
     import hairfastgan_b200.postprocess as P

@@ -158,3 +158,59 @@ def test_postprocess_feature_iresnet(N, golden_dir):
     record("pp_feature_iresnet_64", rel_max_err=e2, ref_rms=rms2)
     assert yl.shape == (1, 512, 64, 64) and e2 < TOL_ENC[dtype_name()], e2
     assert torch.equal(yl, fr(xl.cuda()))             # deterministic
+
+
+def test_bisenet_glue_kernels(N):
+    """7x7 stem, max pooling, pooled 1x1 conv, gated add + nearest upsample, bilinear logit upsample vs torch fp32."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 3, 64, 96, generator=g) * 2 - 1
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.1
+    bn = torch.nn.BatchNorm2d(64).eval()
+    bn.weight.data.uniform_(0.5, 1.5, generator=g); bn.bias.data.normal_(0, 0.2, generator=g)
+    bn.running_mean.normal_(0, 0.2, generator=g); bn.running_var.uniform_(0.5, 1.5, generator=g)
+    ref = F.relu(bn(F.conv2d(x, w, stride=2, padding=3)))
+    y16 = N.stem7x7s2(x.cuda(), w.cuda(), bn.cuda())
+    assert y16.shape == (2, 32, 48, 64)
+    assert float((N.to_nchw32(y16).cpu() - ref).abs().max()) < 3e-2 * float(ref.abs().max())
+    yr = N.to_nchw32(y16).cpu()                                         # 16-bit rounded copy = exact glue input
+    mp = N.to_nchw32(N.maxpool3x3s2(y16)).cpu()
+    assert torch.equal(mp, F.max_pool2d(yr, 3, 2, 1))
+    wfc = torch.randn(40, 64, 1, 1, generator=g) * 0.3
+    sc, sh = torch.rand(40, generator=g) + 0.5, torch.randn(40, generator=g) * 0.2
+    m = yr.mean((2, 3))
+    for act, fn in ((0, lambda t: t), (1, F.relu), (2, torch.sigmoid)):
+        got = N.pooled_fc(y16, wfc.cuda(), sc.cuda(), sh.cuda(), act=act).cpu()
+        assert float((got - fn(F.linear(m, wfc.view(40, 64)) * sc + sh)).abs().max()) < 1e-4
+    gate, addv = torch.rand(2, 64, generator=g), torch.randn(2, 64, generator=g)
+    t16 = N.to_nhwc16(torch.randn(2, 64, 32, 48, generator=g).cuda())
+    tr = N.to_nchw32(t16).cpu()
+    up = N.to_nchw32(N.gate_add_up(y16, gate=gate.cuda(), addvec=addv.cuda(), addt16=t16, up=2)).cpu()
+    refu = F.interpolate(yr * gate.view(2, 64, 1, 1) + addv.view(2, 64, 1, 1) + tr, scale_factor=2, mode="nearest")
+    assert up.shape == (2, 64, 64, 96) and float((up - refu).abs().max()) < 4e-2
+    lo = torch.randn(2, 32, 8, 12, generator=g)
+    bu = N.bilinear_upsample_nchw(lo.cuda(), 19, 64, 96).cpu()
+    assert float((bu - F.interpolate(lo[:, :19], (64, 96), mode="bilinear", align_corners=True)).abs().max()) < 1e-5
+
+
+def test_bisenet_golden(N, golden_dir):
+    """BiSeNet(n_classes=19) (face_parsing/model.py:217-244) vs the reference golden."""
+    import hairfastgan_b200.bisenet as B
+    g = np.load(os.path.join(golden_dir, "bisenet.npz"))
+    net = B.BiSeNet(n_classes=19).eval()
+    net.load_state_dict(EO.synth_params_like(net, seed=51), strict=True)
+    net = net.cuda()
+    x = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(52)) * 2 - 1
+    out, out16, out32 = net(x.cuda())
+    assert out.shape == out16.shape == out32.shape == (2, 19, 256, 256)
+    e, rms = rel_err(out[:, :, ::4, ::4], torch.from_numpy(g["out_sub"]))
+    e16, _ = rel_err(out16[:, :, ::8, ::8], torch.from_numpy(g["out16_sub"]))
+    e32, _ = rel_err(out32[:, :, ::8, ::8], torch.from_numpy(g["out32_sub"]))
+    low = net(x.cuda(), return_lowres=True)
+    el, _ = rel_err(low[0], torch.from_numpy(g["low_out"]))
+    record("bisenet", out_rel_max_err=e, out16_rel_max_err=e16, out32_rel_max_err=e32, low_rel_max_err=el, ref_rms=rms)
+    assert max(e, e16, e32, el) < TOL_ENC[dtype_name()], (e, e16, e32, el)
+    assert torch.equal(out, net(x.cuda())[0])          # deterministic
+    ref_label = torch.from_numpy(g["out_sub"]).argmax(1)
+    agree = float((out[:, :, ::4, ::4].cpu().argmax(1) == ref_label).float().mean())
+    record("bisenet_argmax_agreement", agreement=agree)
+    assert agree > 0.97
