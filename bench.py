@@ -11,8 +11,9 @@ calls batched together (independent triples, BASELINE config 5):
     (720.5 + 208.7 GFLOP),
   * the PostProcess conv stack: FeatureEncoderMult on 2 images at 256^2 and FeatureiResnet on the
     concatenated 1024-channel 64^2 content maps (180.2 + 594.3 GFLOP),
-i.e. 2761.3 algorithmic GFLOP per triple.  Not in the step: stage glue (resizes, masks, lerps) and the out-of-scope
-nets (BiSeNet / SEAN / CLIP / mask nets).  `value` times the step with inputs resident in HBM;
+  * BiSeNet face parsing on 3 images at 512^2 and 2 at 1024^2 (302.5 GFLOP),
+i.e. 3063.8 algorithmic GFLOP per triple.  Not in the step: stage glue (resizes, masks, lerps) and the out-of-scope
+nets (SEAN / CLIP / mask nets).  `value` times the step with inputs resident in HBM;
 `e2e` times it through the public Python API with HOST (pinned) inputs copied in and the T final images
 copied out inside the timed region.
 
@@ -40,8 +41,10 @@ GFLOP_E4E_IMG, GFLOP_FSE_IMG = 144.1, 69.6                # SURVEY 8a rows a13 /
 GFLOP_ENC_PER_TRIPLE = 5 * GFLOP_E4E_IMG + 3 * GFLOP_FSE_IMG
 GFLOP_PP_ENC_IMG, GFLOP_PP_RES = 90.1, 594.3              # PostProcess FeatureEncoderMult / FeatureiResnet
 GFLOP_PP_PER_TRIPLE = 2 * GFLOP_PP_ENC_IMG + GFLOP_PP_RES
-GFLOP_PER_TRIPLE = GFLOP_GEN_PER_TRIPLE + GFLOP_ENC_PER_TRIPLE + GFLOP_PP_PER_TRIPLE      # = 2761.3
-GFLOP_CPU_SAMPLE = GFLOP_FULL + GFLOP_E4E_IMG + GFLOP_FSE_IMG + GFLOP_PP_ENC_IMG + GFLOP_PP_RES   # = 1046.6
+GFLOP_SEG_512 = 27.5                                      # BiSeNet (ResNet-18 context path + heads) on one 512^2 image
+GFLOP_SEG_PER_TRIPLE = 3 * GFLOP_SEG_512 + 2 * 4 * GFLOP_SEG_512      # 3 calls at 512^2, 2 at 1024^2
+GFLOP_PER_TRIPLE = GFLOP_GEN_PER_TRIPLE + GFLOP_ENC_PER_TRIPLE + GFLOP_PP_PER_TRIPLE + GFLOP_SEG_PER_TRIPLE   # = 3063.8
+GFLOP_CPU_SAMPLE = GFLOP_FULL + GFLOP_E4E_IMG + GFLOP_FSE_IMG + GFLOP_PP_ENC_IMG + GFLOP_PP_RES + GFLOP_SEG_512  # 1074.1
 ROOFLINE_US_PER_IMG = 142.5                               # SURVEY Appendix A, sum of per-layer maxima
 
 
@@ -136,14 +139,16 @@ def run_ours(args, rank, world, local_rank):
     for name, prm in pp_res.named_parameters():      # keep the 6 stacked residual blocks O(1) with random weights
         if name.endswith("bn3.weight") or name.endswith("downsample.1.weight"):
             prm.data.mul_(0.3)
-    for net in (e4e, fse, pp_enc, pp_res):            # non-trivial BatchNorm statistics
+    import hairfastgan_b200.bisenet as SEG
+    seg = SEG.BiSeNet(n_classes=19).to(dev).eval()    # my_parsing_util.py:42
+    for net in (e4e, fse, pp_enc, pp_res, seg):       # non-trivial BatchNorm statistics
         for m in net.modules():
             if isinstance(m, torch.nn.BatchNorm2d):
                 m.running_var.uniform_(0.5, 1.5)
                 m.running_mean.normal_(0, 0.1)
     bcast_bytes = 0
     if world > 1:                                     # weights replicated: one NCCL broadcast at init
-        for net in (gen, e4e, fse, pp_enc, pp_res):
+        for net in (gen, e4e, fse, pp_enc, pp_res, seg):
             bcast_bytes += sharding.broadcast_module_(net, src=0)
     calls = census(T)
     g = torch.Generator(device="cpu").manual_seed(100 + rank)
@@ -151,6 +156,9 @@ def run_ours(args, rank, world, local_rank):
     host_lin = [None if r is None else torch.randn(b, 512, r, r, generator=g).pin_memory() for (_, _, b, r) in calls]
     # 256^2 network inputs: e4e (3T), e4e (2T), FSE (3T), PostProcess source (T) and target (T)
     host_img = [(torch.rand(n * T, 3, 256, 256, generator=g) * 2 - 1).pin_memory() for n in (3, 2, 3, 1, 1)]
+    # BiSeNet inputs: the three 512^2 images of a triple (Embedding.py:81) and two 1024^2 ones (Alignment / Blending)
+    host_img += [(torch.rand(3 * T, 3, 512, 512, generator=g) * 2 - 1).pin_memory(),
+                 (torch.rand(T, 3, 1024, 1024, generator=g) * 2 - 1).pin_memory()]
     dev_lat = [t.to(dev) for t in host_lat]
     dev_lin = [None if t is None else t.to(dev) for t in host_lin]
     dev_img = [t.to(dev) for t in host_img]
@@ -172,6 +180,8 @@ def run_ours(args, rank, world, local_rank):
         _, (f_face,) = pp_enc(img[3])                  # PostProcessModel.forward, models/Encoders.py:120-139
         _, (f_hair,) = pp_enc(img[4])
         pp_res(torch.cat((f_face, f_hair), dim=1))
+        seg(img[5])                                    # get_segmentation x3 at 512^2 (models/Net.py:108-115)
+        seg(img[6]); seg(img[6])                       # and twice at 1024^2
         launches[0] += lib.hf_total_launch_count() - n0
         if e2e:
             host_out.copy_(final, non_blocking=True)
@@ -253,6 +263,12 @@ def run_ours(args, rank, world, local_rank):
                                     "feature_iresnet_tflops_algorithmic": round(16 * GFLOP_PP_RES / ms_ppr, 1),
                                     "feature_iresnet_ms": round(ms_ppr, 3)}
         del xr
+        # BiSeNet at 512^2, B=16
+        xs = torch.rand(16, 3, 512, 512, device=dev) * 2 - 1
+        ms_seg = avg_ms(lambda: seg(xs))
+        extra["bisenet_b16_512"] = {"img_per_s": round(16e3 / ms_seg, 1),
+                                    "tflops_algorithmic": round(16 * GFLOP_SEG_512 / ms_seg, 1)}
+        del xs
         extra["roofline"] = roofline
         extra["roofline_b4"] = roofline_b4
     if world > 1:
@@ -303,8 +319,9 @@ def time_dominant_kernel(gen, dev, B=4):
 
 def cpu_oracle_sample(threads=None):
     """The reference algorithm on host cores (oracle port; the Python reference cannot travel to the GPU box): one
-    full 1024^2 generator forward + one e4e + one FSE + one PostProcess FeatureEncoderMult forward and the
-    PostProcess FeatureiResnet, B=1 (1046.6 of the 2761.3 GFLOP of a triple), scaled to triples/s."""
+    full 1024^2 generator forward + one e4e + one FSE + one PostProcess FeatureEncoderMult forward, the PostProcess
+    FeatureiResnet and one BiSeNet forward at 512^2, B=1 (1074.1 of the 3063.8 GFLOP of a triple), scaled to
+    triples/s."""
     import torch
     from oracle import stylegan2_oracle as O
     from oracle import encoders_oracle as EO
@@ -322,7 +339,12 @@ def cpu_oracle_sample(threads=None):
     pr = EO.synth_params_like(PP.FeatureiResnet([[1024, 2], [768, 2], [512, 2]]), 41)
     x = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(12)) * 2 - 1
     xr = torch.randn(1, 1024, 64, 64, generator=torch.Generator().manual_seed(13))
+    from oracle import bisenet_oracle as BO
+    import hairfastgan_b200.bisenet as SEG
+    ps = EO.synth_params_like(SEG.BiSeNet(n_classes=19), 51)
+    xs = torch.rand(1, 3, 512, 512, generator=torch.Generator().manual_seed(14)) * 2 - 1
     t0 = time.perf_counter()
+    BO.bisenet_ref(ps, xs)
     O.generator_ref(p, lat, noise)
     EO.e4e_ref(pe, x)
     EO.fse_ref(pf, x)
@@ -366,10 +388,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = ("SURVEY-8 hot path of HairFast.swap(): 8 Generator.forward calls (1024^2, randomize_noise=True) + "
                 "e4e on 5 and FSE on 3 images (256^2) + PostProcess conv stack (FeatureEncoderMult x2, FeatureiResnet "
-                "@64^2) per triple = 2761.3 GFLOP/triple (SURVEY App. B / 8d config 3), synthetic weights; "
-                "out-of-scope nets (BiSeNet/SEAN/CLIP/mask) and stage glue excluded")
+                "@64^2) + BiSeNet on 3 images at 512^2 and 2 at 1024^2 per triple = 3063.8 GFLOP/triple (SURVEY "
+                "App. B / 8d config 3 / 8f-3), synthetic weights; out-of-scope nets (SEAN/CLIP/mask) and stage glue "
+                "excluded")
     sample = ("one full 1024^2 generator forward + one e4e + one FSE + one FeatureEncoderMult forward + the "
-              "FeatureiResnet, B=1 = 1046.6 of 2761.3 GFLOP per triple, scaled")
+              "FeatureiResnet + one BiSeNet forward at 512^2, B=1 = 1074.1 of 3063.8 GFLOP per triple, scaled")
 
     if args.impl == "reference":
         if rank != 0:

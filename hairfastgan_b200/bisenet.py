@@ -193,7 +193,7 @@ class BiSeNet(nn.Module):
             return {"conv": conv, "shift": shift, "w": m.conv_atten.weight, "a_scale": a_scale, "a_shift": a_shift}
 
         avg_scale, avg_shift = nn16.bn_affine(cp.conv_avg.bn)
-        pk = {"key": key,
+        pk = {"key": key, "stem": nn16.PackedStem7x7(rn.conv1.weight, rn.bn1),
               "blocks": [[_PackedBlock(b) for b in layer] for layer in (rn.layer1, rn.layer2, rn.layer3, rn.layer4)],
               "arm16": arm(cp.arm16), "arm32": arm(cp.arm32),
               "head32": cp.conv_head32.packed(), "head16": cp.conv_head16.packed(),
@@ -214,9 +214,8 @@ class BiSeNet(nn.Module):
         if H % 32 or W % 32:
             raise NotImplementedError(f"BiSeNet: input size {H}x{W} must be a multiple of 32")
         pk = self._pack()
-        rn = self.cp.resnet
         # ---- Resnet18 (resnet.py:68-79)
-        f = nn16.maxpool3x3s2(nn16.stem7x7s2(x, rn.conv1.weight, rn.bn1))
+        f = nn16.maxpool3x3s2(pk["stem"](x))
         feats = []
         for li, layer in enumerate(pk["blocks"]):
             for blk in layer:

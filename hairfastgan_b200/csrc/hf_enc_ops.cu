@@ -231,8 +231,8 @@ __global__ void __launch_bounds__(256) scale_add_kernel(const uint16_t* __restri
                                                         const float* __restrict__ s2, const float* __restrict__ b2,
                                                         uint16_t* __restrict__ y, uint16_t* __restrict__ yb, int H,
                                                         int W, int C, int64_t total2) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total2; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e = i * 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)total2; i += gridDim.x * blockDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions
+    const int64_t e = (int64_t)i * 2;
     const int c = (int)(e % C);
     int64_t t = e / C;
     const int x = (int)(t % W); t /= W;
@@ -265,13 +265,13 @@ __global__ void __launch_bounds__(256) scale_add_vec8_kernel(const uint16_t* __r
                                                              uint16_t* __restrict__ y, uint16_t* __restrict__ yb, int H,
                                                              int W, int C8, int64_t total8) {
   const int C = C8 * 8;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)total8; i += gridDim.x * blockDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions
     const int c = (int)(i % C8) * 8;
-    int64_t t = i / C8;
+    int t = i / C8;
     const int x = (int)(t % W); t /= W;
     const int yy = (int)(t % H);
     const int b = (int)(t / H);
-    const uint4 r = __ldg(reinterpret_cast<const uint4*>(res + i * 8));
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(res + (size_t)i * 8));
     const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
     float v[8];
 #pragma unroll
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) scale_add_vec8_kernel(const uint16_t* __r
       uint4 o;
       o.x = Half2T<DT>::pack(v[0], v[1]); o.y = Half2T<DT>::pack(v[2], v[3]);
       o.z = Half2T<DT>::pack(v[4], v[5]); o.w = Half2T<DT>::pack(v[6], v[7]);
-      *reinterpret_cast<uint4*>(y + i * 8) = o;
+      *reinterpret_cast<uint4*>(y + (size_t)i * 8) = o;
     }
     if (yb) {
       float a[8], d[8];
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256) scale_add_vec8_kernel(const uint16_t* __r
       o.y = Half2T<DT>::pack(fmaf(v[2], a[2], d[2]), fmaf(v[3], a[3], d[3]));
       o.z = Half2T<DT>::pack(fmaf(v[4], a[4], d[4]), fmaf(v[5], a[5], d[5]));
       o.w = Half2T<DT>::pack(fmaf(v[6], a[6], d[6]), fmaf(v[7], a[7], d[7]));
-      *reinterpret_cast<uint4*>(yb + i * 8) = o;
+      *reinterpret_cast<uint4*>(yb + (size_t)i * 8) = o;
     }
   }
 }
@@ -321,6 +321,7 @@ int launch_scale_add(const void* res16, const float* se, const void* shortcut16,
   HF_REQUIRE(C % 2 == 0 && (sc_stride == 1 || sc_stride == 2), "scale_add: bad C / stride");
   if (C % 8 == 0) {
     const int64_t total8 = (int64_t)B * H * W * C / 8;
+    HF_REQUIRE(total8 < (int64_t)2000000000, "tensor too large for one launch (%lld work items): split the batch", (long long)total8);
     const int grid8 = (int)std::min<int64_t>((total8 + 255) / 256, (int64_t)num_sms() * 16);
     if (dtype == HF_BF16)
       scale_add_vec8_kernel<HF_BF16><<<grid8, 256, 0, st>>>((const uint16_t*)res16, se, (const uint16_t*)shortcut16,
@@ -335,6 +336,7 @@ int launch_scale_add(const void* res16, const float* se, const void* shortcut16,
     return HF_OK;
   }
   const int64_t total2 = (int64_t)B * H * W * C / 2;
+  HF_REQUIRE(total2 < (int64_t)2000000000, "tensor too large for one launch (%lld work items): split the batch", (long long)total2);
   const int grid = (int)std::min<int64_t>((total2 + 255) / 256, (int64_t)num_sms() * 16);
   if (dtype == HF_BF16)
     scale_add_kernel<HF_BF16><<<grid, 256, 0, st>>>((const uint16_t*)res16, se, (const uint16_t*)shortcut16, sc_stride,
@@ -353,8 +355,8 @@ __global__ void __launch_bounds__(256) upsample_add_kernel(const uint16_t* __res
                                                            uint16_t* __restrict__ out, int h, int w, int H, int W, int C,
                                                            int64_t total2) {
   const float ry = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, rx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total2; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e = i * 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)total2; i += gridDim.x * blockDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions
+    const int64_t e = (int64_t)i * 2;
     const int c = (int)(e % C);
     int64_t t = e / C;
     const int X = (int)(t % W); t /= W;
@@ -394,9 +396,9 @@ __global__ void __launch_bounds__(256) upsample_add_vec8_kernel(const uint16_t* 
                                                                 int C8, int64_t total8) {
   const int C = C8 * 8;
   const float ry = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, rx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)total8; i += gridDim.x * blockDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions
     const int c = (int)(i % C8) * 8;
-    int64_t t = i / C8;
+    int t = i / C8;
     const int X = (int)(t % W); t /= W;
     const int Y = (int)(t % H);
     const int b = (int)(t / H);
@@ -410,14 +412,14 @@ __global__ void __launch_bounds__(256) upsample_add_vec8_kernel(const uint16_t* 
     unpack8<DT>(__ldg(reinterpret_cast<const uint4*>(x + base + ((size_t)y0 * w + x1) * C)), a01);
     unpack8<DT>(__ldg(reinterpret_cast<const uint4*>(x + base + ((size_t)y1 * w + x0) * C)), a10);
     unpack8<DT>(__ldg(reinterpret_cast<const uint4*>(x + base + ((size_t)y1 * w + x1) * C)), a11);
-    unpack8<DT>(__ldg(reinterpret_cast<const uint4*>(y + i * 8)), yy);
+    unpack8<DT>(__ldg(reinterpret_cast<const uint4*>(y + (size_t)i * 8)), yy);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       v[k] = (1.f - ly) * ((1.f - lx) * a00[k] + lx * a01[k]) + ly * ((1.f - lx) * a10[k] + lx * a11[k]) + yy[k];
     uint4 o;
     o.x = Half2T<DT>::pack(v[0], v[1]); o.y = Half2T<DT>::pack(v[2], v[3]);
     o.z = Half2T<DT>::pack(v[4], v[5]); o.w = Half2T<DT>::pack(v[6], v[7]);
-    *reinterpret_cast<uint4*>(out + i * 8) = o;
+    *reinterpret_cast<uint4*>(out + (size_t)i * 8) = o;
   }
 }
 
@@ -426,6 +428,7 @@ int launch_upsample_add(const void* x16, const void* y16, void* out16, int B, in
   HF_REQUIRE(x16 && y16 && out16 && C % 2 == 0, "upsample_add: bad arguments");
   if (C % 8 == 0) {
     const int64_t total8 = (int64_t)B * H * W * C / 8;
+    HF_REQUIRE(total8 < (int64_t)2000000000, "tensor too large for one launch (%lld work items): split the batch", (long long)total8);
     const int grid8 = (int)std::min<int64_t>((total8 + 255) / 256, (int64_t)num_sms() * 16);
     if (dtype == HF_BF16)
       upsample_add_vec8_kernel<HF_BF16><<<grid8, 256, 0, st>>>((const uint16_t*)x16, (const uint16_t*)y16,
@@ -438,6 +441,7 @@ int launch_upsample_add(const void* x16, const void* y16, void* out16, int B, in
     return HF_OK;
   }
   const int64_t total2 = (int64_t)B * H * W * C / 2;
+  HF_REQUIRE(total2 < (int64_t)2000000000, "tensor too large for one launch (%lld work items): split the batch", (long long)total2);
   const int grid = (int)std::min<int64_t>((total2 + 255) / 256, (int64_t)num_sms() * 16);
   if (dtype == HF_BF16)
     upsample_add_kernel<HF_BF16><<<grid, 256, 0, st>>>((const uint16_t*)x16, (const uint16_t*)y16, (uint16_t*)out16, h,
@@ -454,7 +458,7 @@ int launch_upsample_add(const void* x16, const void* y16, void* out16, int B, in
 template <int DT>
 __global__ void __launch_bounds__(256) adaptive_avgpool_kernel(const uint16_t* __restrict__ x, float* __restrict__ y,
                                                                int H, int W, int C, int oh, int ow, int64_t total) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)total; i += gridDim.x * blockDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions
     const int c = (int)(i % C);
     int64_t t = i / C;
     const int ox = (int)(t % ow); t /= ow;
@@ -520,6 +524,7 @@ int launch_adaptive_avgpool(const void* x16, float* y, int B, int H, int W, int 
     return HF_OK;
   }
   const int64_t total = (int64_t)B * oh * ow * C;
+  HF_REQUIRE(total < (int64_t)2000000000, "tensor too large for one launch (%lld work items): split the batch", (long long)total);
   const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
   if (dtype == HF_BF16)
     adaptive_avgpool_kernel<HF_BF16><<<grid, 256, 0, st>>>((const uint16_t*)x16, y, H, W, C, oh, ow, total);

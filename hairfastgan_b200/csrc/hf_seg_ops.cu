@@ -28,80 +28,53 @@ __device__ __forceinline__ uint4 pack8s(const float* v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Resnet18.conv1 + bn1 + relu (resnet.py:60-61,69-70): 7x7, stride 2, pad 3, 3 -> 64 channels, fp32 NCHW in,
-// 16-bit NHWC out.  w = [147][64] fp32 (tap-major, BatchNorm scale folded), shift[64].
-// CTA = 16x16 output pixels: the 37x37x3 input patch and the weights live in shared memory; one thread = one pixel
-// x 64 channels (64 accumulators; weights are broadcast LDS.128).  K = 147 is too thin for the tensor-core path
-// (Cin = 3 would be padded to 32 per tap: 11x wasted MMA work) and the layer is 1.2 GFLOP per 512^2 image.
+// Resnet18.conv1 (resnet.py:60,69): 7x7, stride 2, pad 3 on 3 channels.  K = 147 per output pixel is too thin for an
+// implicit-GEMM tap loop (Cin = 3 would be padded to 32 per tap: 11x wasted MMA work) and the first, direct SIMT
+// version ran at 30 TFLOP/s fp32 = 26 % of a BiSeNet forward.  So the stem is an explicit im2col into a 16-bit NHWC
+// tensor [B,Ho,Wo,160] (channel k = (c*7 + ky)*7 + kx, zero above 147 and outside the image) followed by the
+// ordinary 1x1 tensor-core convolution with the folded BatchNorm + ReLU epilogue.  One thread = 8 channels of one pixel.
 // ------------------------------------------------------------------------------------------------
-constexpr int kStemT = 16, kStemP = 2 * kStemT + 5;      // 37
+constexpr int kStemK = 147, kStemKPad = 160;
 
 template <int DT>
-__global__ void __launch_bounds__(256) stem7x7_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                      const float* __restrict__ shift, uint16_t* __restrict__ y, int H,
-                                                      int W, int Ho, int Wo) {
-  extern __shared__ float sm[];
-  float* sw = sm;                              // [147][64]
-  float* sx = sm + 147 * 64;                   // [3][37][37]
-  const int b = blockIdx.z, oy0 = blockIdx.y * kStemT, ox0 = blockIdx.x * kStemT;
-  for (int i = threadIdx.x; i < 147 * 64; i += 256) sw[i] = __ldg(w + i);
-  const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
-  for (int i = threadIdx.x; i < 3 * kStemP * kStemP; i += 256) {
-    const int c = i / (kStemP * kStemP), r = (i / kStemP) % kStemP, q = i % kStemP;
-    const int yy = iy0 + r, xx = ix0 + q;
-    sx[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + (((size_t)b * 3 + c) * H + yy) * W + xx) : 0.f;
-  }
-  __syncthreads();
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  float acc[64];
+__global__ void __launch_bounds__(256) im2col7x7s2_kernel(const float* __restrict__ x, uint16_t* __restrict__ y, int H,
+                                                          int W, int Ho, int Wo, int64_t total) {
+  const int plane = H * W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)total; i += gridDim.x * blockDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions
+    const int k0 = (int)(i % (kStemKPad / 8)) * 8;
+    int t = i / (kStemKPad / 8);
+    const int ox = (int)(t % Wo); t /= Wo;
+    const int oy = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const float* xb = x + (size_t)b * 3 * plane;
+    // decode (c, ky, kx) once, then walk: kx fastest, then ky, then c
+    int c = k0 / 49, r = k0 - c * 49, ky = r / 7, kx = r - ky * 7;
+    const int ybase = 2 * oy - 3, xbase = 2 * ox - 3;
+    float v[8];
 #pragma unroll
-  for (int o = 0; o < 64; ++o) acc[o] = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < 3; ++c) {
-#pragma unroll 1
-    for (int ky = 0; ky < 7; ++ky) {
-      const float* row = sx + (c * kStemP + 2 * ty + ky) * kStemP + 2 * tx;
-#pragma unroll
-      for (int kx = 0; kx < 7; ++kx) {
-        const float v = row[kx];
-        const float4* wp = reinterpret_cast<const float4*>(sw + ((c * 7 + ky) * 7 + kx) * 64);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float4 ww = wp[q];
-          acc[4 * q] = fmaf(v, ww.x, acc[4 * q]); acc[4 * q + 1] = fmaf(v, ww.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(v, ww.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v, ww.w, acc[4 * q + 3]);
-        }
-      }
+    for (int j = 0; j < 8; ++j) {
+      float val = 0.f;
+      const int yy = ybase + ky, xx = xbase + kx;
+      if (c < 3 && (unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) val = __ldg(xb + c * plane + yy * W + xx);
+      v[j] = val;
+      if (++kx == 7) { kx = 0; if (++ky == 7) { ky = 0; ++c; } }
     }
-  }
-  const int oy = oy0 + ty, ox = ox0 + tx;
-  if (oy < Ho && ox < Wo) {
-    uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)b * Ho + oy) * Wo + ox) * 64);
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      float v[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = fmaxf(acc[g * 8 + k] + __ldg(shift + g * 8 + k), 0.f);
-      dst[g] = pack8s<DT>(v);
-    }
+    *reinterpret_cast<uint4*>(y + (size_t)i * 8) = pack8s<DT>(v);
   }
 }
 
-int launch_stem7x7(const float* x, const float* w, const float* shift, void* y16, int B, int H, int W, int dtype,
-                   cudaStream_t st) {
-  HF_REQUIRE(x && w && shift && y16, "stem7x7: null pointer");
-  HF_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "stem7x7: bad shape");
-  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
-  const size_t smem = (size_t)(147 * 64 + 3 * kStemP * kStemP) * sizeof(float);
-  dim3 grid(cdiv_s(Wo, kStemT), cdiv_s(Ho, kStemT), B);
-  if (dtype == HF_BF16) {
-    HF_CUDA_OK(cudaFuncSetAttribute(stem7x7_kernel<HF_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stem7x7_kernel<HF_BF16><<<grid, 256, smem, st>>>(x, w, shift, (uint16_t*)y16, H, W, Ho, Wo);
-  } else {
-    HF_CUDA_OK(cudaFuncSetAttribute(stem7x7_kernel<HF_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stem7x7_kernel<HF_F16><<<grid, 256, smem, st>>>(x, w, shift, (uint16_t*)y16, H, W, Ho, Wo);
-  }
-  HF_LAUNCH_OK("stem7x7");
+int launch_im2col7x7s2(const float* x, void* y16, int B, int H, int W, int dtype, cudaStream_t st) {
+  HF_REQUIRE(x && y16, "im2col7x7s2: null pointer");
+  HF_REQUIRE(B > 0 && H > 0 && W > 0, "im2col7x7s2: bad shape");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const int64_t total = (int64_t)B * Ho * Wo * (kStemKPad / 8);
+  HF_REQUIRE(total < (int64_t)2000000000, "tensor too large for one launch (%lld work items): split the batch", (long long)total);
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 32);
+  if (dtype == HF_BF16)
+    im2col7x7s2_kernel<HF_BF16><<<grid, 256, 0, st>>>(x, (uint16_t*)y16, H, W, Ho, Wo, total);
+  else
+    im2col7x7s2_kernel<HF_F16><<<grid, 256, 0, st>>>(x, (uint16_t*)y16, H, W, Ho, Wo, total);
+  HF_LAUNCH_OK("im2col7x7s2");
   count_launch();
   return HF_OK;
 }
@@ -113,9 +86,9 @@ template <int DT>
 __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y,
                                                            int H, int W, int Ho, int Wo, int C8, int64_t total8) {
   const int C = C8 * 8;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)total8; i += gridDim.x * blockDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions
     const int c = (int)(i % C8) * 8;
-    int64_t t = i / C8;
+    int t = i / C8;
     const int ox = (int)(t % Wo); t /= Wo;
     const int oy = (int)(t % Ho);
     const int b = (int)(t / Ho);
@@ -136,7 +109,7 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const uint16_t* __res
         for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], v[k]);
       }
     }
-    *reinterpret_cast<uint4*>(y + i * 8) = pack8s<DT>(m);
+    *reinterpret_cast<uint4*>(y + (size_t)i * 8) = pack8s<DT>(m);
   }
 }
 
@@ -144,6 +117,7 @@ int launch_maxpool3x3s2(const void* x16, void* y16, int B, int H, int W, int C, 
   HF_REQUIRE(x16 && y16 && C % 8 == 0 && B > 0 && H > 0 && W > 0, "maxpool: bad arguments");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const int64_t total8 = (int64_t)B * Ho * Wo * C / 8;
+  HF_REQUIRE(total8 < (int64_t)2000000000, "tensor too large for one launch (%lld work items): split the batch", (long long)total8);
   const int grid = (int)std::min<int64_t>((total8 + 255) / 256, (int64_t)num_sms() * 16);
   if (dtype == HF_BF16)
     maxpool3x3s2_kernel<HF_BF16><<<grid, 256, 0, st>>>((const uint16_t*)x16, (uint16_t*)y16, H, W, Ho, Wo, C / 8, total8);
@@ -211,9 +185,9 @@ __global__ void __launch_bounds__(256) gate_add_up_kernel(const uint16_t* __rest
                                                           const uint16_t* __restrict__ addt, uint16_t* __restrict__ y,
                                                           int h, int w, int up, int C8, int64_t total8) {
   const int C = C8 * 8, H = h * up, W = w * up;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)total8; i += gridDim.x * blockDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions
     const int c = (int)(i % C8) * 8;
-    int64_t t = i / C8;
+    int t = i / C8;
     const int X = (int)(t % W); t /= W;
     const int Y = (int)(t % H);
     const int b = (int)(t / H);
@@ -234,7 +208,7 @@ __global__ void __launch_bounds__(256) gate_add_up_kernel(const uint16_t* __rest
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] += a[k];
     }
-    *reinterpret_cast<uint4*>(y + i * 8) = pack8s<DT>(v);
+    *reinterpret_cast<uint4*>(y + (size_t)i * 8) = pack8s<DT>(v);
   }
 }
 
@@ -242,6 +216,7 @@ int launch_gate_add_up(const void* x16, const float* gate, const float* addvec, 
                        int h, int w, int C, int up, int dtype, cudaStream_t st) {
   HF_REQUIRE(x16 && y16 && C % 8 == 0 && (up == 1 || up == 2) && B > 0 && h > 0 && w > 0, "gate_add_up: bad arguments");
   const int64_t total8 = (int64_t)B * h * up * w * up * C / 8;
+  HF_REQUIRE(total8 < (int64_t)2000000000, "tensor too large for one launch (%lld work items): split the batch", (long long)total8);
   const int grid = (int)std::min<int64_t>((total8 + 255) / 256, (int64_t)num_sms() * 16);
   if (dtype == HF_BF16)
     gate_add_up_kernel<HF_BF16><<<grid, 256, 0, st>>>((const uint16_t*)x16, gate, addvec, (const uint16_t*)addt16,
@@ -259,11 +234,66 @@ int launch_gate_add_up(const void* x16, const float* gate, const float* addvec, 
 // Cin channel planes of x (the logit convolution pads its 19 classes to 32 output channels).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bilinear_up_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int C,
-                                                               int Cin, int h, int w, int H, int W, int64_t total) {
+                                                               int Cin, int h, int w, int H, int W4, int64_t total4) {
+  // one thread = 4 consecutive output columns of one row (float4 store).  The two source rows are blended first
+  // (per source column), then the columns: for upsampling the 4 outputs touch at most 3 source columns, so this is
+  // 6 loads instead of 16 (same weights as F.interpolate; the association of the fp32 products differs by ~1 ulp).
+  const int W = W4 * 4;
   const float ry = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, rx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)total4; i += gridDim.x * blockDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions
+    const int X0 = (int)(i % W4) * 4;
+    int t = i / W4;
+    const int Y = (int)(t % H); t /= H;
+    const int c = (int)(t % C);
+    const int b = (int)(t / C);
+    const float fy = Y * ry;
+    const int y0 = (int)fy;
+    const int y1 = y0 + 1 < h ? y0 + 1 : y0;
+    const float ly = fy - y0;
+    const float* p0 = x + (((size_t)b * Cin + c) * h + y0) * w;
+    const float* p1 = x + (((size_t)b * Cin + c) * h + y1) * w;
+    const int xa = (int)(X0 * rx);                      // leftmost source column of this strip
+    float o[4];
+    if (rx <= 0.5f) {                                   // strip spans source columns xa .. xa+2
+      float col[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int xs = xa + k < w ? xa + k : w - 1;
+        col[k] = (1.f - ly) * __ldg(p0 + xs) + ly * __ldg(p1 + xs);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float fx = (X0 + j) * rx;
+        const int x0 = (int)fx;
+        const float lx = fx - x0;
+        const int d = x0 - xa;                          // 0..2
+        const float v0 = d == 0 ? col[0] : (d == 1 ? col[1] : col[2]);
+        const float v1 = x0 + 1 < w ? (d == 0 ? col[1] : (d == 1 ? col[2] : col[3])) : v0;
+        o[j] = (1.f - lx) * v0 + lx * v1;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float fx = (X0 + j) * rx;
+        const int x0 = (int)fx;
+        const int x1 = x0 + 1 < w ? x0 + 1 : x0;
+        const float lx = fx - x0;
+        const float v0 = (1.f - ly) * __ldg(p0 + x0) + ly * __ldg(p1 + x0);
+        const float v1 = (1.f - ly) * __ldg(p0 + x1) + ly * __ldg(p1 + x1);
+        o[j] = (1.f - lx) * v0 + lx * v1;
+      }
+    }
+    *reinterpret_cast<float4*>(y + (size_t)i * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256) bilinear_up_nchw_scalar_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                      int C, int Cin, int h, int w, int H, int W,
+                                                                      int64_t total) {
+  const float ry = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, rx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)total; i += gridDim.x * blockDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions
     const int X = (int)(i % W);
-    int64_t t = i / W;
+    int t = i / W;
     const int Y = (int)(t % H); t /= H;
     const int c = (int)(t % C);
     const int b = (int)(t / C);
@@ -282,8 +312,14 @@ int launch_bilinear_up_nchw(const float* x, float* y, int B, int C, int Cin, int
                             cudaStream_t st) {
   HF_REQUIRE(x && y && B > 0 && C > 0 && Cin >= C && h > 0 && w > 0 && H > 0 && W > 0, "bilinear_up: bad arguments");
   const int64_t total = (int64_t)B * C * H * W;
-  const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 32);
-  bilinear_up_nchw_kernel<<<grid, 256, 0, st>>>(x, y, C, Cin, h, w, H, W, total);
+  HF_REQUIRE(total < (int64_t)2000000000, "tensor too large for one launch (%lld work items): split the batch", (long long)total);
+  if (W % 4 == 0 && (((uintptr_t)y) & 15) == 0) {
+    const int grid = (int)std::min<int64_t>((total / 4 + 255) / 256, (int64_t)num_sms() * 32);
+    bilinear_up_nchw_kernel<<<grid, 256, 0, st>>>(x, y, C, Cin, h, w, H, W / 4, total / 4);
+  } else {
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 32);
+    bilinear_up_nchw_scalar_kernel<<<grid, 256, 0, st>>>(x, y, C, Cin, h, w, H, W, total);
+  }
   HF_LAUNCH_OK("bilinear_up_nchw");
   count_launch();
   return HF_OK;

@@ -165,21 +165,35 @@ def adaptive_avgpool(x16, oh: int, ow: int, dtype: Optional[int] = None):
 
 
 # ------------------------------------------------------------------------------------------------ BiSeNet glue
+class PackedStem7x7:
+    """Resnet18.conv1 + bn1 + ReLU (face_parsing/resnet.py:60-61,69-70) = im2col (K = 147, padded to 160) + a 1x1
+    tensor-core convolution with the BatchNorm folded in."""
+
+    def __init__(self, weight: torch.Tensor, bn: torch.nn.BatchNorm2d, dtype: Optional[int] = None):
+        self.dtype = default_dtype() if dtype is None else dtype
+        scale, self.shift = bn_affine(bn)
+        cout = weight.shape[0]
+        self.conv = PackedConv2d(_f32(weight).reshape(cout, 147, 1, 1), scale, cin_pad=160, dtype=self.dtype)
+
+    def __call__(self, x: torch.Tensor):
+        """[B,3,H,W] fp32 NCHW -> [B,Ho,Wo,cout] 16-bit NHWC."""
+        if not x.is_cuda:
+            raise RuntimeError("stem7x7s2: input must be a CUDA tensor (no CPU fallback)")
+        xf = _f32(x)
+        b, c, h, w = xf.shape
+        if c != 3:
+            raise ValueError("stem7x7s2: expected a 3-channel image")
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        cols = torch.empty(b, ho, wo, 160, device=x.device, dtype=torch_dtype(self.dtype))
+        _lib.use_device(x.device.index)
+        _lib.check(_lib.lib().hf_im2col7x7s2_nhwc16(xf.data_ptr(), cols.data_ptr(), b, h, w, self.dtype, _lib.stream_ptr()),
+                   "hf_im2col7x7s2_nhwc16")
+        y, _, _ = self.conv(cols, shift=self.shift, act=3)
+        return y
+
+
 def stem7x7s2(x: torch.Tensor, weight: torch.Tensor, bn: torch.nn.BatchNorm2d, dtype: Optional[int] = None):
-    """Resnet18.conv1 + bn1 + ReLU (face_parsing/resnet.py:60-61,69-70): [B,3,H,W] fp32 -> [B,Ho,Wo,64] 16-bit NHWC."""
-    if not x.is_cuda:
-        raise RuntimeError("stem7x7s2: input must be a CUDA tensor (no CPU fallback)")
-    dt = default_dtype() if dtype is None else dtype
-    scale, shift = bn_affine(bn)
-    wt = (_f32(weight) * scale.view(-1, 1, 1, 1)).reshape(64, 147).t().contiguous()       # [147][64], BN scale folded
-    xf = _f32(x)
-    b, _, h, w = xf.shape
-    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
-    y = torch.empty(b, ho, wo, 64, device=x.device, dtype=torch_dtype(dt))
-    _lib.use_device(x.device.index)
-    _lib.check(_lib.lib().hf_stem7x7s2_forward(xf.data_ptr(), wt.data_ptr(), shift.data_ptr(), y.data_ptr(), b, h, w, dt,
-                                               _lib.stream_ptr()), "hf_stem7x7s2_forward")
-    return y
+    return PackedStem7x7(weight, bn, dtype)(x)
 
 
 def maxpool3x3s2(x16: torch.Tensor, dtype: Optional[int] = None):
