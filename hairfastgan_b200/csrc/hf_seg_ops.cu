@@ -34,32 +34,45 @@ __device__ __forceinline__ uint4 pack8s(const float* v) {
 // tensor [B,Ho,Wo,160] (channel k = (c*7 + ky)*7 + kx, zero above 147 and outside the image) followed by the
 // ordinary 1x1 tensor-core convolution with the folded BatchNorm + ReLU epilogue.  One thread = 8 channels of one pixel.
 // ------------------------------------------------------------------------------------------------
-constexpr int kStemK = 147, kStemKPad = 160;
+constexpr int kStemK = 147, kStemKPad = 160, kI2cTile = 128;
 
 template <int DT>
 __global__ void __launch_bounds__(256) im2col7x7s2_kernel(const float* __restrict__ x, uint16_t* __restrict__ y, int H,
                                                           int W, int Ho, int Wo, int64_t total) {
+  // one CTA per output row (b, oy) (grid-stride): the only runtime-divisor divisions are per row; inside the row
+  // the (ox, 8-channel chunk) split divides by the constant 20
+  // The 21 input row segments (3 channels x 7 rows, zero filled outside the image) of a 128-pixel tile are staged in
+  // shared memory with coalesced loads; every thread then gathers 8 consecutive k from there.
+  __shared__ float sx[21][kI2cTile * 2 + 6];
   const int plane = H * W;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)total; i += gridDim.x * blockDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions
-    const int k0 = (int)(i % (kStemKPad / 8)) * 8;
-    int t = i / (kStemKPad / 8);
-    const int ox = (int)(t % Wo); t /= Wo;
-    const int oy = (int)(t % Ho);
-    const int b = (int)(t / Ho);
+  const int rows = (int)total;                 // = B * Ho
+  constexpr int CH = kStemKPad / 8, SW = kI2cTile * 2 + 6;
+  const int xtiles = (Wo + kI2cTile - 1) / kI2cTile;
+  for (int work = blockIdx.x; work < rows * xtiles; work += gridDim.x) {
+    const int row = work / xtiles, ox0 = (work - row * xtiles) * kI2cTile;
+    const int b = row / Ho, oy = row - b * Ho;
     const float* xb = x + (size_t)b * 3 * plane;
-    // decode (c, ky, kx) once, then walk: kx fastest, then ky, then c
-    int c = k0 / 49, r = k0 - c * 49, ky = r / 7, kx = r - ky * 7;
-    const int ybase = 2 * oy - 3, xbase = 2 * ox - 3;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float val = 0.f;
-      const int yy = ybase + ky, xx = xbase + kx;
-      if (c < 3 && (unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) val = __ldg(xb + c * plane + yy * W + xx);
-      v[j] = val;
-      if (++kx == 7) { kx = 0; if (++ky == 7) { ky = 0; ++c; } }
+    const int ybase = 2 * oy - 3, xbase = 2 * ox0 - 3;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 21 * SW; i += blockDim.x) {
+      const int rr = i / SW, q = i - rr * SW;
+      const int c = rr / 7, yy = ybase + (rr - c * 7), xx = xbase + q;
+      sx[rr][q] = ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) ? __ldg(xb + c * plane + yy * W + xx) : 0.f;
     }
-    *reinterpret_cast<uint4*>(y + (size_t)i * 8) = pack8s<DT>(v);
+    __syncthreads();
+    const int npix = min(kI2cTile, Wo - ox0);
+    uint16_t* ytile = y + ((size_t)row * Wo + ox0) * kStemKPad;
+    for (int idx = threadIdx.x; idx < npix * CH; idx += blockDim.x) {
+      const int oxl = idx / CH, k0 = (idx - oxl * CH) * 8;
+      int rr = k0 / 7, kx = k0 - rr * 7;             // rr = c*7 + ky; walk kx fastest
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = rr < 21 ? sx[rr][2 * oxl + kx] : 0.f;
+        if (++kx == 7) { kx = 0; ++rr; }
+      }
+      *reinterpret_cast<uint4*>(ytile + (size_t)idx * 8) = pack8s<DT>(v);
+    }
   }
 }
 
@@ -67,9 +80,11 @@ int launch_im2col7x7s2(const float* x, void* y16, int B, int H, int W, int dtype
   HF_REQUIRE(x && y16, "im2col7x7s2: null pointer");
   HF_REQUIRE(B > 0 && H > 0 && W > 0, "im2col7x7s2: bad shape");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  const int64_t total = (int64_t)B * Ho * Wo * (kStemKPad / 8);
-  HF_REQUIRE(total < (int64_t)2000000000, "tensor too large for one launch (%lld work items): split the batch", (long long)total);
-  const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 32);
+  const int64_t total = (int64_t)B * Ho;         // output rows
+  HF_REQUIRE(total < (int64_t)2000000000, "tensor too large for one launch (%lld rows): split the batch", (long long)total);
+  const int64_t work = total * ((Wo + kI2cTile - 1) / kI2cTile);
+  HF_REQUIRE(work < (int64_t)2000000000, "im2col7x7s2: too many tiles (%lld): split the batch", (long long)work);
+  const int grid = (int)std::min<int64_t>(work, (int64_t)num_sms() * 16);
   if (dtype == HF_BF16)
     im2col7x7s2_kernel<HF_BF16><<<grid, 256, 0, st>>>(x, (uint16_t*)y16, H, W, Ho, Wo, total);
   else
@@ -234,56 +249,38 @@ int launch_gate_add_up(const void* x16, const float* gate, const float* addvec, 
 // Cin channel planes of x (the logit convolution pads its 19 classes to 32 output channels).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bilinear_up_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int C,
-                                                               int Cin, int h, int w, int H, int W4, int64_t total4) {
-  // one thread = 4 consecutive output columns of one row (float4 store).  The two source rows are blended first
-  // (per source column), then the columns: for upsampling the 4 outputs touch at most 3 source columns, so this is
-  // 6 loads instead of 16 (same weights as F.interpolate; the association of the fp32 products differs by ~1 ulp).
+                                                               int Cin, int h, int w, int H, int W4, int64_t rows) {
+  // One CTA per output row (b, c, Y), grid-stride.  The two source rows are blended once into shared memory
+  // (w values), then every thread produces 4 consecutive output columns (float4 store) from it.  Same weights as
+  // F.interpolate(align_corners=True); the association of the fp32 products differs by ~1 ulp.
+  extern __shared__ float srow[];
   const int W = W4 * 4;
   const float ry = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, rx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)total4; i += gridDim.x * blockDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions
-    const int X0 = (int)(i % W4) * 4;
-    int t = i / W4;
-    const int Y = (int)(t % H); t /= H;
-    const int c = (int)(t % C);
-    const int b = (int)(t / C);
+  for (int row = blockIdx.x; row < (int)rows; row += gridDim.x) {
+    const int bc = row / H, Y = row - bc * H;
+    const int b = bc / C, c = bc - b * C;
     const float fy = Y * ry;
     const int y0 = (int)fy;
     const int y1 = y0 + 1 < h ? y0 + 1 : y0;
     const float ly = fy - y0;
     const float* p0 = x + (((size_t)b * Cin + c) * h + y0) * w;
     const float* p1 = x + (((size_t)b * Cin + c) * h + y1) * w;
-    const int xa = (int)(X0 * rx);                      // leftmost source column of this strip
-    float o[4];
-    if (rx <= 0.5f) {                                   // strip spans source columns xa .. xa+2
-      float col[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int xs = xa + k < w ? xa + k : w - 1;
-        col[k] = (1.f - ly) * __ldg(p0 + xs) + ly * __ldg(p1 + xs);
-      }
+    __syncthreads();
+    for (int xs = threadIdx.x; xs < w; xs += blockDim.x) srow[xs] = (1.f - ly) * __ldg(p0 + xs) + ly * __ldg(p1 + xs);
+    __syncthreads();
+    float* yrow = y + (size_t)row * W;
+    for (int X4 = threadIdx.x; X4 < W4; X4 += blockDim.x) {
+      float o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float fx = (X0 + j) * rx;
-        const int x0 = (int)fx;
-        const float lx = fx - x0;
-        const int d = x0 - xa;                          // 0..2
-        const float v0 = d == 0 ? col[0] : (d == 1 ? col[1] : col[2]);
-        const float v1 = x0 + 1 < w ? (d == 0 ? col[1] : (d == 1 ? col[2] : col[3])) : v0;
-        o[j] = (1.f - lx) * v0 + lx * v1;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float fx = (X0 + j) * rx;
+        const float fx = (X4 * 4 + j) * rx;
         const int x0 = (int)fx;
         const int x1 = x0 + 1 < w ? x0 + 1 : x0;
         const float lx = fx - x0;
-        const float v0 = (1.f - ly) * __ldg(p0 + x0) + ly * __ldg(p1 + x0);
-        const float v1 = (1.f - ly) * __ldg(p0 + x1) + ly * __ldg(p1 + x1);
-        o[j] = (1.f - lx) * v0 + lx * v1;
+        o[j] = (1.f - lx) * srow[x0] + lx * srow[x1];
       }
+      *reinterpret_cast<float4*>(yrow + X4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
     }
-    *reinterpret_cast<float4*>(y + (size_t)i * 4) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -313,9 +310,10 @@ int launch_bilinear_up_nchw(const float* x, float* y, int B, int C, int Cin, int
   HF_REQUIRE(x && y && B > 0 && C > 0 && Cin >= C && h > 0 && w > 0 && H > 0 && W > 0, "bilinear_up: bad arguments");
   const int64_t total = (int64_t)B * C * H * W;
   HF_REQUIRE(total < (int64_t)2000000000, "tensor too large for one launch (%lld work items): split the batch", (long long)total);
-  if (W % 4 == 0 && (((uintptr_t)y) & 15) == 0) {
-    const int grid = (int)std::min<int64_t>((total / 4 + 255) / 256, (int64_t)num_sms() * 32);
-    bilinear_up_nchw_kernel<<<grid, 256, 0, st>>>(x, y, C, Cin, h, w, H, W / 4, total / 4);
+  if (W % 4 == 0 && (((uintptr_t)y) & 15) == 0 && w <= 8192) {
+    const int64_t rows = (int64_t)B * C * H;
+    const int grid = (int)std::min<int64_t>(rows, (int64_t)num_sms() * 16);
+    bilinear_up_nchw_kernel<<<grid, 256, (size_t)w * sizeof(float), st>>>(x, y, C, Cin, h, w, H, W / 4, rows);
   } else {
     const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 32);
     bilinear_up_nchw_scalar_kernel<<<grid, 256, 0, st>>>(x, y, C, Cin, h, w, H, W, total);
