@@ -269,6 +269,23 @@ def run_ours(args, rank, world, local_rank):
         extra["bisenet_b16_512"] = {"img_per_s": round(16e3 / ms_seg, 1),
                                     "tflops_algorithmic": round(16 * GFLOP_SEG_512 / ms_seg, 1)}
         del xs
+        # SURVEY 8d metric (3): the standalone HBM-bound operators (module-level API a6 / a7), GB/s = (in + out) / time
+        import hairfastgan_b200.op as OP
+        hbm = peaks()["hbm_gbs"]
+        xa = torch.randn(4, 64, 1024, 1024, device=dev); ba = torch.randn(64, device=dev)
+        ms_a = avg_ms(lambda: OP.fused_leaky_relu(xa, ba))
+        kern = torch.tensor([1., 3., 3., 1.], device=dev)
+        k2 = kern[None, :] * kern[:, None]; k2 = k2 / k2.sum()
+        xu = torch.randn(1, 256, 1025, 1025, device=dev)
+        ms_u1 = avg_ms(lambda: OP.upfirdn2d(xu, k2 * 4, pad=(1, 1)))
+        xs3 = torch.randn(48, 3, 512, 512, device=dev)
+        ms_u2 = avg_ms(lambda: OP.upfirdn2d(xs3, k2 * 4, up=2, pad=(2, 1)))
+        gbs = {"fused_leaky_relu_4x64x1024x1024": 2 * xa.numel() * 4 / ms_a / 1e6,
+               "upfirdn2d_up1_k4_pad11_256x1025x1025": (xu.numel() + 256 * 1024 * 1024) * 4 / ms_u1 / 1e6,
+               "upfirdn2d_up2_k4_pad21_144x512x512": (xs3.numel() * 5) * 4 / ms_u2 / 1e6}
+        extra["ops_hbm"] = {k: {"GB/s": round(v, 1), "frac_of_measured_copy_peak": round(v / hbm, 3)}
+                            for k, v in gbs.items()}
+        del xa, xu, xs3
         extra["roofline"] = roofline
         extra["roofline_b4"] = roofline_b4
     if world > 1:

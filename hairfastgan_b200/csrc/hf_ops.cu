@@ -22,8 +22,8 @@ __global__ void __launch_bounds__(256) upfirdn2d_up1_k4_kernel(const float* __re
   constexpr int TW = 64;
   constexpr int IN_ROWS = (ROWS - 1) * DOWN + 4;
   constexpr int IN_COLS = (TW - 1) * DOWN + 4;
-  constexpr int PITCH = IN_COLS + 1;
-  __shared__ float tile[IN_ROWS * PITCH];
+  constexpr int PITCH = (IN_COLS + 3) / 4 * 4;          // rows start 16-byte aligned: the window is read as float4
+  __shared__ __align__(16) float tile[IN_ROWS * PITCH];
   __shared__ float kf[16];
   const int plane = blockIdx.z;
   const int oy0 = blockIdx.y * ROWS, ox0 = blockIdx.x * TW;
@@ -50,10 +50,14 @@ __global__ void __launch_bounds__(256) upfirdn2d_up1_k4_kernel(const float* __re
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky) {
-      const float* row = tile + (r * DOWN + ky) * PITCH + tx * 4 * DOWN;
-      float w[3 * DOWN + 4];
+      const float4* row4 = reinterpret_cast<const float4*>(tile + (r * DOWN + ky) * PITCH + tx * 4 * DOWN);
+      constexpr int NW4 = (3 * DOWN + 4 + 3) / 4;
+      float w[NW4 * 4];
 #pragma unroll
-      for (int i = 0; i < 3 * DOWN + 4; ++i) w[i] = row[i];
+      for (int i = 0; i < NW4; ++i) {
+        const float4 t4 = row4[i];
+        w[4 * i] = t4.x; w[4 * i + 1] = t4.y; w[4 * i + 2] = t4.z; w[4 * i + 3] = t4.w;
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -73,7 +77,8 @@ __global__ void __launch_bounds__(256) upfirdn2d_up1_k4_kernel(const float* __re
 }
 
 // Fast path: up = 2, down = 1, 4x4 taps (the RGB-skip Upsample, model.py:35-53).  Only 2x2 of the
-// 16 taps hit a non-zero sample; each thread makes 4 consecutive outputs of one row.
+// 16 taps hit a non-zero sample; each thread makes 4 consecutive outputs of one row.  (A row-per-CTA variant with
+// the two live input rows staged in shared memory measured slower: 1.06 vs 1.41 TB/s.)
 __global__ void __launch_bounds__(256) upfirdn2d_up2_k4_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                const float* __restrict__ k, int in_h, int in_w,
                                                                int out_h, int out_w, int px0, int py0,
@@ -82,12 +87,12 @@ __global__ void __launch_bounds__(256) upfirdn2d_up2_k4_kernel(const float* __re
   if (threadIdx.x < 16) kf[threadIdx.x] = k[15 - threadIdx.x];
   __syncthreads();
   const int quads_per_row = (out_w + 3) >> 2;
-  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total_quads;
-       q += (int64_t)gridDim.x * blockDim.x) {
-    int qx = (int)(q % quads_per_row);
-    int64_t t = q / quads_per_row;
-    int oy = (int)(t % out_h);
-    int plane = (int)(t / out_h);
+  // 32-bit index math (the launcher checks total_quads < 2^31)
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < (int)total_quads; q += gridDim.x * blockDim.x) {
+    int qx = q % quads_per_row;
+    int t = q / quads_per_row;
+    int oy = t % out_h;
+    int plane = t / out_h;
     const float* xp = x + (size_t)plane * in_h * in_w;
     const int ky0 = (py0 - oy) & 1;          // oy + ky - py0 must be even
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -173,9 +178,10 @@ int launch_upfirdn2d(const float* x, float* y, const float* k, int planes, int i
       dim3 grid(cdiv(out_w, 64), cdiv(out_h, 16), planes);
       upfirdn2d_up1_k4_kernel<2, 16><<<grid, 256, 0, st>>>(x, y, k, in_h, in_w, out_h, out_w, px0, py0);
     }
-  } else if (k4 && sym && up_x == 2 && down_x == 1) {
+  } else if (k4 && sym && up_x == 2 && down_x == 1 &&
+             (int64_t)planes * out_h * ((out_w + 3) / 4) < (int64_t)2000000000) {
     int64_t quads = (int64_t)planes * out_h * ((out_w + 3) / 4);
-    int grid = (int)std::min<int64_t>((quads + 255) / 256, (int64_t)num_sms() * 16);
+    int grid = (int)std::min<int64_t>((quads + 255) / 256, (int64_t)num_sms() * 32);
     upfirdn2d_up2_k4_kernel<<<grid, 256, 0, st>>>(x, y, k, in_h, in_w, out_h, out_w, px0, py0, quads);
   } else {
     int64_t total = (int64_t)planes * out_h * out_w;
@@ -219,9 +225,40 @@ __global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__
   }
 }
 
+// Plane form of the vector path: blockIdx.y = (batch, channel) plane, so the bias index is computed once per CTA
+// instead of two 64-bit divisions per float4 (measured: the flat form ran at about a third of the HBM rate).
+__global__ void __launch_bounds__(256) bias_act_plane_kernel(const float* __restrict__ x, const float* __restrict__ b,
+                                                             float* __restrict__ y, int quads_per_plane, int size_b,
+                                                             int act, float alpha, float scale) {
+  const int plane = blockIdx.y;
+  const float bb = size_b ? __ldg(b + plane % size_b) : 0.f;
+  const float4* xp = reinterpret_cast<const float4*>(x) + (size_t)plane * quads_per_plane;
+  float4* yp = reinterpret_cast<float4*>(y) + (size_t)plane * quads_per_plane;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < quads_per_plane; i += gridDim.x * blockDim.x) {
+    const float4 v = __ldg(xp + i);
+    float r[4] = {v.x + bb, v.y + bb, v.z + bb, v.w + bb};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = r[j];
+      if (act == 3) t = (t > 0.f) ? t : t * alpha;
+      r[j] = t * scale;
+    }
+    yp[i] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
 int launch_bias_act(const float* x, const float* b, float* y, int64_t n, int size_b, int64_t step_b, int act,
                     float alpha, float scale, cudaStream_t st) {
   if (n == 0) return HF_OK;
+  if (x && y && (size_b == 0 || b) && (act == 1 || act == 3) && step_b % 4 == 0 && step_b >= 1024 && n % step_b == 0 &&
+      n / step_b <= 65535 && step_b / 4 < (int64_t)2000000000 && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0)) {
+    const int planes = (int)(n / step_b), quads = (int)(step_b / 4);
+    const int gx = std::max(1, std::min(cdiv(quads, 256), std::max(1, num_sms() * 16 / planes)));
+    bias_act_plane_kernel<<<dim3(gx, planes), 256, 0, st>>>(x, b, y, quads, size_b, act, alpha, scale);
+    HF_LAUNCH_OK("bias_act");
+    count_launch();
+    return HF_OK;
+  }
   HF_REQUIRE(x && y, "bias_act: null pointer");
   HF_REQUIRE(act == 1 || act == 3, "bias_act: act must be 1 (linear) or 3 (leaky relu), got %d", act);
   HF_REQUIRE(n >= 0 && size_b >= 0 && step_b >= 1, "bias_act: bad sizes");
@@ -492,16 +529,16 @@ __global__ void __launch_bounds__(256) rgb_combine_vec4_kernel(const float* part
   if (threadIdx.x < 16) kf[threadIdx.x] = upk ? upk[15 - threadIdx.x] : 0.f;
   __syncthreads();
   const int h2 = H >> 1, w2 = W >> 1, wq = W >> 2;
-  for (int64_t i4 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i4 < total4;
-       i4 += (int64_t)gridDim.x * blockDim.x) {
-    const int q = (int)(i4 % wq);
-    const int64_t t = i4 / wq;
-    const int Y = (int)(t % H);
-    const int plane = (int)(t / H);
+  // 32-bit index math (the launcher checks total4 < 2^31): a 64-bit div/mod costs ~100 instructions
+  for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < (int)total4; i4 += gridDim.x * blockDim.x) {
+    const int q = i4 % wq;
+    const int t = i4 / wq;
+    const int Y = t % H;
+    const int plane = t / H;
     const float bv = bias ? __ldg(bias + plane % 3) : 0.f;
     float acc[4] = {bv, bv, bv, bv};
     for (int s = 0; s < num_partials; ++s) {
-      const float4 v = *reinterpret_cast<const float4*>(partial + s * partial_stride + i4 * 4);   // may alias rgb
+      const float4 v = *reinterpret_cast<const float4*>(partial + s * partial_stride + (size_t)i4 * 4);   // may alias rgb
       acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
     }
     if (skip) {
@@ -530,7 +567,7 @@ __global__ void __launch_bounds__(256) rgb_combine_vec4_kernel(const float* part
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[j] += up[j];
     }
-    *reinterpret_cast<float4*>(rgb + i4 * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(rgb + (size_t)i4 * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
 }
 
@@ -539,7 +576,7 @@ int launch_rgb_combine(const float* partial, int num_partials, const float* bias
   HF_REQUIRE(rgb && (partial || num_partials == 0), "rgb_combine: null pointer");
   HF_REQUIRE(!skip || up_kernel, "rgb_combine: skip given without an upsample kernel");
   int64_t total = (int64_t)B * 3 * H * W;
-  if (W % 4 == 0 && ((((uintptr_t)partial | (uintptr_t)rgb) & 15) == 0)) {
+  if (W % 4 == 0 && ((((uintptr_t)partial | (uintptr_t)rgb) & 15) == 0) && total / 4 < (int64_t)2000000000) {
     int64_t total4 = total / 4;
     int grid = (int)std::min<int64_t>((total4 + 255) / 256, (int64_t)num_sms() * 16);
     rgb_combine_vec4_kernel<<<grid, 256, 0, st>>>(partial, num_partials, total, bias, skip, up_kernel, rgb, H, W,
