@@ -165,16 +165,14 @@ def run_ours(args, rank, world, local_rank):
     host_out = torch.empty(T, 3, 1024, 1024).pin_memory()
     launches = [0]
 
-    def step(e2e: bool):
-        img = [t.to(dev, non_blocking=True) for t in host_img] if e2e else dev_img
+    def compute(img, lats, lins):
+        """The hot path of T triples through the public module API (what swap()'s stages call)."""
         n0 = lib.hf_total_launch_count()
         for net, x in ((e4e, img[0]), (e4e, img[1]), (fse, img[2])):   # Embedding.py:71,74 / :51
             net(x)
         final = None
         for i, (s, e, b, r) in enumerate(calls):
-            lat = host_lat[i].to(dev, non_blocking=True) if e2e else dev_lat[i]
-            lin = None if r is None else (host_lin[i].to(dev, non_blocking=True) if e2e else dev_lin[i])
-            out = gen([lat], input_is_latent=True, start_layer=s, end_layer=e, layer_in=lin)   # random noise, as swap()
+            out = gen([lats[i]], input_is_latent=True, start_layer=s, end_layer=e, layer_in=lins[i])   # random noise
             if i == len(calls) - 1:
                 final = out[0]
         _, (f_face,) = pp_enc(img[3])                  # PostProcessModel.forward, models/Encoders.py:120-139
@@ -183,15 +181,16 @@ def run_ours(args, rank, world, local_rank):
         seg(img[5])                                    # get_segmentation x3 at 512^2 (models/Net.py:108-115)
         seg(img[6]); seg(img[6])                       # and twice at 1024^2
         launches[0] += lib.hf_total_launch_count() - n0
-        if e2e:
-            host_out.copy_(final, non_blocking=True)
         return final
+
+    def step(_e2e: bool = False):
+        return compute(dev_img, dev_lat, dev_lin)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
-    def timed(e2e: bool, steps: int, warmup: int):
+    def timed(_e2e: bool, steps: int, warmup: int):
         for _ in range(warmup):
-            step(e2e)
+            step()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -202,7 +201,7 @@ def run_ours(args, rank, world, local_rank):
             flush.fill_(1)                                             # L2 flush between timed iterations
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            step(e2e)
+            step()
             e1.record()
             e1.synchronize()
             total_ms += e0.elapsed_time(e1)
@@ -210,6 +209,57 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
         return sharding.max_over_ranks(total_ms, dev), launches[0]
+
+    # ---- end to end: HOST inputs in, HOST images out, every step.  The way a caller would drive the public API:
+    # uploads on one side stream, the result download on another, double-buffered, so that the copies of step k+1 / k-1
+    # overlap the kernels of step k.  The timed region is ONE event pair around all K steps (L2 flushes included) and
+    # ends only after the last download has finished.
+    h2d_stream, d2h_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    host_all = host_img + host_lat + [t for t in host_lin if t is not None]
+    dbuf = [[torch.empty(t.shape, device=dev) for t in host_all] for _ in range(2)]
+    hout = [host_out, torch.empty(T, 3, 1024, 1024).pin_memory()]
+    ev_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    n_img, n_lat = len(host_img), len(host_lat)
+
+    def e2e_step(k: int):
+        s = k & 1
+        with torch.cuda.stream(h2d_stream):
+            h2d_stream.wait_event(ev_done[s])          # step k-2 no longer reads this buffer set
+            for d, h in zip(dbuf[s], host_all):
+                d.copy_(h, non_blocking=True)
+            ev_ready[s].record(h2d_stream)
+        main_stream.wait_event(ev_ready[s])
+        it = iter(dbuf[s][n_img + n_lat:])
+        lins = [None if t is None else next(it) for t in host_lin]
+        final = compute(dbuf[s][:n_img], dbuf[s][n_img:n_img + n_lat], lins)
+        ev_done[s].record(main_stream)
+        final.record_stream(d2h_stream)
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(ev_done[s])
+            hout[s].copy_(final, non_blocking=True)
+
+    def timed_e2e(steps: int, warmup: int):
+        for k in range(warmup):
+            e2e_step(k)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main_stream)
+        for k in range(steps):
+            flush.fill_(1)
+            e2e_step(k)
+        main_stream.wait_stream(d2h_stream)            # the last image is on the host when the clock stops
+        main_stream.wait_stream(h2d_stream)
+        e1.record(main_stream)
+        e1.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return sharding.max_over_ranks(e0.elapsed_time(e1), dev)
 
     if args.profile_step:                             # for `ncu --profile-from-start off`: exactly one step
         step(False)
@@ -228,7 +278,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     first = sampler.mark()
     ms, n_launch = timed(False, args.steps, args.warmup)
-    ms_e2e, _ = timed(True, args.steps, max(3, args.warmup // 2))
+    ms_e2e = timed_e2e(args.steps, max(3, args.warmup // 2))
     clocks = sampler.stop(first) if rank == 0 else None
 
     extra = {"nccl_broadcast_bytes_at_init": bcast_bytes}
@@ -448,7 +498,8 @@ def main():
         "dtype": os.environ.get("HAIRFAST_DTYPE", "bf16") + " operands, f32 accumulate", "data": "synthetic",
         "config": {"workload": workload, "triples_per_step_per_gpu": T, "size": 1024,
                    "parallelism": f"dp{world} (independent triples per rank, no step collective)",
-                   "l2": "256 MiB flush write between timed steps; per-step CUDA events summed"},
+                   "l2": "256 MiB flush write between timed steps; value: per-step CUDA events summed; e2e: one event "
+                         "pair around all steps, uploads/downloads double-buffered on side streams"},
         "tflops_algorithmic": round(GFLOP_PER_TRIPLE * value / 1e3, 1),
         "e2e": {"value": round(e2e_value, 3), "unit": "triples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": T * 3 * 1024 * 1024 * 4},
