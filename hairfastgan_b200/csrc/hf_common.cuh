@@ -175,66 +175,8 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-// Warp-collective variants: executed convergently by all 32 lanes with warp-uniform operands; one lane
-// is elected INSIDE the asm block.  Keeping the control flow uniform lets the compiler hold the
-// descriptors in uniform registers instead of wrapping every UTCHMMA in an R2UR waterfall loop (measured:
-// the `if (lane == 0)` form cost ~450 issue cycles per conv tap, see profiles/).
-__device__ __forceinline__ void umma_f16_warp(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                              uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-      ::"r"(smem_u32(bar))
-      : "memory");
-}
-// All NK (= channels-per-chunk / 16) MMAs of one conv tap in ONE asm block: a single elect, descriptor low
-// words advanced by 2 (= 32 bytes = 16 K-elements) inside PTX.  a_lo/b_lo are descriptor low words
-// ((addr >> 4) | LBO), a_hi/b_hi the loop-invariant high words.  acc_first = 0 zero-initialises the
-// accumulator on the first MMA only.
-template <int NK>
-__device__ __forceinline__ void umma_tap_warp(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
-                                              uint32_t b_hi, uint32_t idesc, uint32_t acc_first) {
-  static_assert(NK == 2 || NK == 4, "NK must be 2 or 4");
-  if (NK == 4) {
-    asm volatile(
-        "{\n\t.reg .pred p, q, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
-        "elect.sync _|q, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "setp.eq.b32 t, 0, 0;\n\t"
-        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-        "add.u32 al, %1, 2;\n\tadd.u32 bl, %3, 2;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
-        "add.u32 al, %1, 4;\n\tadd.u32 bl, %3, 4;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
-        "add.u32 al, %1, 6;\n\tadd.u32 bl, %3, 6;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t}"
-        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p, q, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
-        "elect.sync _|q, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "setp.eq.b32 t, 0, 0;\n\t"
-        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-        "add.u32 al, %1, 2;\n\tadd.u32 bl, %3, 2;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t}"
-        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first)
-        : "memory");
-  }
-}
+// The MMA main loops run inside ONE elected lane (`if (elect_one()) { ... }`, CUTLASS style): issuing under
+// `if (lane == 0)` made ptxas wrap every UTCHMMA in an R2UR waterfall loop (~450 issue cycles per conv tap, measured).
 // Single-thread forms, to be used inside `if (elect_one()) { ... }` (CUTLASS style: the whole MMA main loop
 // runs in ONE elected lane, so ptxas needs neither waterfall loops nor per-instruction elect/vote).
 __device__ __forceinline__ bool elect_one() {
