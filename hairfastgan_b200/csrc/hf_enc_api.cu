@@ -155,6 +155,13 @@ int hf_gate_add_up_nhwc16(const void* x16, const float* gate, const float* addve
                             (cudaStream_t)stream);
 }
 
+int hf_bicubic_downsample_f32(const float* x, const float* kernel, float* y, int planes, int height, int width,
+                              int factor, int clip_round, void* stream) {
+  int rc = ensure_device_current();
+  if (rc) return rc;
+  return launch_bicubic_down(x, kernel, y, planes, height, width, factor, clip_round, (cudaStream_t)stream);
+}
+
 int hf_bilinear_upsample_nchw_f32(const float* x, float* y, int batch, int channels, int in_channels, int h, int w,
                                   int height, int width, void* stream) {
   int rc = ensure_device_current();

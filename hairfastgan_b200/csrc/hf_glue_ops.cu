@@ -1,0 +1,77 @@
+// Stage glue around the networks: BicubicDownSample (utils/bicubic.py:6-78), the separable
+// 4*factor-tap bicubic decimation HairFast applies to every 1024^2 image (Embedding.py:66-67, Blending.py:64).
+// HBM-bound SIMT, fp32, deterministic.
+#include <algorithm>
+
+#include "hf_kernels.cuh"
+
+namespace hf {
+
+constexpr int kBicTileH = 8, kBicTileW = 64, kBicMaxFactor = 8;
+
+__device__ __forceinline__ int reflect_index(int i, int n) {      // F.pad(mode='reflect'): edge not repeated
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// y[p, oy, ox] = sum_j k[j] * V[oy][ox*f + j - pl],  V[oy][c] = sum_i k[i] * x[p, refl(oy*f + i - pt), refl(c)]
+// (reference order: reflect-pad H, 1-D conv over H with stride f, [clip/round], reflect-pad W, 1-D conv over W).
+// One CTA = 8 x 64 outputs of one plane: the vertical pass of the (64 f + 3 f) needed columns goes to shared memory,
+// the horizontal pass reads it back.
+__global__ void __launch_bounds__(256) bicubic_down_kernel(const float* __restrict__ x, const float* __restrict__ k,
+                                                           float* __restrict__ y, int H, int W, int Ho, int Wo, int f,
+                                                           int clip_round) {
+  extern __shared__ float sm[];
+  const int taps = 4 * f;
+  const int pad = taps - f, p0 = pad / 2;                 // pad_top = pad_left = (4f - f) // 2
+  const int cols = kBicTileW * f + pad;                  // input columns one output row segment needs
+  float* kf = sm;                                        // [taps]
+  float* v = sm + 4 * kBicMaxFactor;                     // [kBicTileH][cols]
+  const int plane = blockIdx.z, oy0 = blockIdx.y * kBicTileH, ox0 = blockIdx.x * kBicTileW;
+  const float* xp = x + (size_t)plane * H * W;
+  if (threadIdx.x < taps) kf[threadIdx.x] = __ldg(k + threadIdx.x);
+  __syncthreads();
+  const int ix0 = ox0 * f - p0;
+  for (int i = threadIdx.x; i < kBicTileH * cols; i += blockDim.x) {
+    const int r = i / cols, c = i - r * cols;
+    const int oy = oy0 + r;
+    float acc = 0.f;
+    if (oy < Ho) {
+      const int xc = reflect_index(ix0 + c, W);
+      const int iy0 = oy * f - p0;
+      for (int t = 0; t < taps; ++t) acc = fmaf(kf[t], __ldg(xp + (size_t)reflect_index(iy0 + t, H) * W + xc), acc);
+      if (clip_round) acc = fminf(fmaxf(rintf(acc), 0.f), 255.f);
+    }
+    v[i] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kBicTileH * kBicTileW; i += blockDim.x) {
+    const int r = i / kBicTileW, c = i - r * kBicTileW;
+    const int oy = oy0 + r, ox = ox0 + c;
+    if (oy >= Ho || ox >= Wo) continue;
+    const float* row = v + r * cols + c * f;
+    float acc = 0.f;
+    for (int t = 0; t < taps; ++t) acc = fmaf(kf[t], row[t], acc);
+    if (clip_round) acc = fminf(fmaxf(rintf(acc), 0.f), 255.f);
+    y[((size_t)plane * Ho + oy) * Wo + ox] = acc;
+  }
+}
+
+int launch_bicubic_down(const float* x, const float* k, float* y, int planes, int H, int W, int factor, int clip_round,
+                        cudaStream_t st) {
+  HF_REQUIRE(x && k && y, "bicubic_down: null pointer");
+  HF_REQUIRE(factor >= 1 && factor <= kBicMaxFactor, "bicubic_down: factor %d unsupported (1..%d)", factor, kBicMaxFactor);
+  HF_REQUIRE(planes > 0 && planes <= 65535 && H > 0 && W > 0, "bicubic_down: bad shape");
+  const int taps = 4 * factor, pad = taps - factor;
+  HF_REQUIRE(pad / 2 < H && pad - pad / 2 < H && pad / 2 < W && pad - pad / 2 < W, "bicubic_down: image smaller than the reflect padding");
+  const int Ho = (H + pad - taps) / factor + 1, Wo = (W + pad - taps) / factor + 1;
+  const size_t smem = (size_t)(4 * kBicMaxFactor + kBicTileH * (kBicTileW * factor + pad)) * sizeof(float);
+  dim3 grid((Wo + kBicTileW - 1) / kBicTileW, (Ho + kBicTileH - 1) / kBicTileH, planes);
+  bicubic_down_kernel<<<grid, 256, smem, st>>>(x, k, y, H, W, Ho, Wo, factor, clip_round);
+  HF_LAUNCH_OK("bicubic_down");
+  count_launch();
+  return HF_OK;
+}
+
+}  // namespace hf

@@ -67,6 +67,8 @@ int launch_pooled_fc(const void* x16, const float* w, const float* scale, const 
                      float* ws, int B, int HW, int C, int Cout, int dtype, cudaStream_t st);
 int launch_gate_add_up(const void* x16, const float* gate, const float* addvec, const void* addt16, void* y16, int B,
                        int h, int w, int C, int up, int dtype, cudaStream_t st);
+int launch_bicubic_down(const float* x, const float* k, float* y, int planes, int H, int W, int factor, int clip_round,
+                        cudaStream_t st);
 int launch_bilinear_up_nchw(const float* x, float* y, int B, int C, int Cin, int h, int w, int H, int W,
                             cudaStream_t st);
 int launch_se_gate(const void* x16, const float* fc1, const float* fc2, float* out, float* ws, int B, int HW, int C,

@@ -24,6 +24,9 @@ After ``install()`` the import statements of the reference resolve to this packa
 * ``from models.CtrlHair.external_code.face_parsing.model import BiSeNet`` (face_parsing/my_parsing_util.py:15)
                                                                                     -> ``hairfastgan_b200.bisenet``
 
+* ``from utils.bicubic import BicubicDownSample`` (models/Embedding.py:13, models/Blending.py:6)
+                                                                                    -> ``hairfastgan_b200.bicubic``
+
 Nothing in the reference tree is edited and its JIT build of the two 2019 CUDA extensions
 (op/fused_act.py:10-16, op/upfirdn2d.py:10-16) never runs.
 """
@@ -54,6 +57,10 @@ _ENCODERS = {
 # (models/CtrlHair/external_code/face_parsing/my_parsing_util.py:15)
 _SEGMENTATION = {
     "models.CtrlHair.external_code.face_parsing.model": "hairfastgan_b200.bisenet",
+}
+# stage glue: `from utils.bicubic import BicubicDownSample` (models/Embedding.py:13, models/Blending.py:6)
+_GLUE = {
+    "utils.bicubic": "hairfastgan_b200.bicubic",
 }
 _created_stubs = []
 
@@ -122,13 +129,17 @@ def _register(ref_name: str, ours: str) -> None:
     sys.modules[ref_name] = importlib.import_module(ours)
 
 
-def install(generator: bool = True, encoders: bool = True, postprocess: bool = True, segmentation: bool = True) -> None:
+def install(generator: bool = True, encoders: bool = True, postprocess: bool = True, segmentation: bool = True,
+            glue: bool = True) -> None:
     """Register the overlay.  ``generator=False`` swaps only the operator package (L1 boundary) and leaves the
     reference's own ``models/stylegan2/model.py`` classes in place on top of our ops; ``encoders=False`` keeps
     the reference's PyTorch encoders; ``postprocess=False`` keeps its PostProcess conv stack; ``segmentation=False``
     its BiSeNet."""
     if segmentation:
         for ref_name, ours in _SEGMENTATION.items():
+            _register(ref_name, ours)
+    if glue:
+        for ref_name, ours in _GLUE.items():
             _register(ref_name, ours)
     for ref_name, ours in _OPS.items():
         _register(ref_name, ours)
@@ -147,7 +158,7 @@ def install(generator: bool = True, encoders: bool = True, postprocess: bool = T
 
 
 def uninstall() -> None:
-    for ref_name in list(_OPS) + list(_GENERATORS) + list(_ENCODERS) + list(_SEGMENTATION) + _created_stubs:
+    for ref_name in list(_OPS) + list(_GENERATORS) + list(_ENCODERS) + list(_SEGMENTATION) + list(_GLUE) + _created_stubs:
         sys.modules.pop(ref_name, None)
     _created_stubs.clear()
     if _patcher in sys.meta_path:

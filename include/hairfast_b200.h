@@ -283,6 +283,14 @@ int hf_gate_add_up_nhwc16(const void* x16, const float* gate, const float* addve
 int hf_bilinear_upsample_nchw_f32(const float* x, float* y, int batch, int channels, int in_channels, int h, int w,
                                   int height, int width, void* stream);
 
+/* ---- stage glue ---- */
+/* BicubicDownSample.forward (utils/bicubic.py:36-78): reflect-pad + separable `4*factor`-tap FIR + decimation by
+ * `factor`, vertical pass first.  x [planes,H,W] -> y [planes,H/factor,W/factor] fp32; kernel [4*factor] = the
+ * normalised taps of BicubicDownSample.__init__ (:20-33); clip_round != 0 applies clamp(round(v), 0, 255) after each
+ * pass (:63-64,68-69).  factor 1..8. */
+int hf_bicubic_downsample_f32(const float* x, const float* kernel, float* y, int planes, int height, int width,
+                              int factor, int clip_round, void* stream);
+
 /* Number of kernels the last hf_generator_forward / hf_conv_forward of this thread launched. */
 int hf_last_launch_count(void);
 /* Number of kernels every hf_* call of this thread has launched since the library was loaded. */

@@ -1,0 +1,52 @@
+"""CPU oracle for the stage glue.  TEST INFRASTRUCTURE ONLY -- same rules as stylegan2_oracle.py.
+
+``bicubic_downsample_ref`` restates ``BicubicDownSample.forward`` (utils/bicubic.py:36-78) in matrix form: with
+D[o, i] = sum of the taps k[t] whose reflect-padded position o*f + t - pad_top lands on input index i, the two padded
+strided 1-D convolutions are  y = D_h @ x @ D_w^T  (vertical pass first, optional clip/round after each pass).
+Pinned by tests/golden/glue.npz (oracle/gen_golden_glue.py runs the unmodified reference class)."""
+from __future__ import annotations
+
+import torch
+
+
+def bicubic_taps(factor: int, a: float = -0.5) -> torch.Tensor:
+    """utils/bicubic.py:7-25: Keys kernel sampled at (i - floor(2f) + 0.5) / f, i < 4f, normalised to sum 1."""
+    size = 4 * factor
+    xs = (torch.arange(size, dtype=torch.float32) - float(size // 2) + 0.5) / factor
+    ax = xs.abs()
+    k = torch.where(ax <= 1., (a + 2.) * ax ** 3 - (a + 3.) * ax ** 2 + 1,
+                    torch.where(ax < 2., a * ax ** 3 - 5. * a * ax ** 2 + 8. * a * ax - 4. * a, torch.zeros_like(ax)))
+    return k / k.sum()
+
+
+def _reflect(i: int, n: int) -> int:
+    if i < 0:
+        i = -i
+    if i >= n:
+        i = 2 * (n - 1) - i
+    return i
+
+
+def decimation_matrix(n: int, factor: int, k: torch.Tensor) -> torch.Tensor:
+    taps = 4 * factor
+    pad = taps - factor
+    p0 = pad // 2
+    n_out = (n + pad - taps) // factor + 1
+    d = torch.zeros(n_out, n, dtype=torch.float64)
+    for o in range(n_out):
+        for t in range(taps):
+            d[o, _reflect(o * factor + t - p0, n)] += float(k[t])
+    return d
+
+
+def bicubic_downsample_ref(x: torch.Tensor, factor: int, clip_round: bool = False) -> torch.Tensor:
+    k = bicubic_taps(factor)
+    dh = decimation_matrix(x.shape[2], factor, k)
+    dw = decimation_matrix(x.shape[3], factor, k)
+    v = torch.einsum("oh,bchw->bcow", dh, x.double())
+    if clip_round:
+        v = torch.clamp(torch.round(v.float()), 0.0, 255.0).double()
+    y = torch.einsum("pw,bcow->bcop", dw, v)
+    if clip_round:
+        y = torch.clamp(torch.round(y.float()), 0.0, 255.0).double()
+    return y.float()

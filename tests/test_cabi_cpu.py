@@ -116,6 +116,8 @@ def test_install_overlay_redirects_reference_imports():
         assert psp.Encoder4Editing.__module__ == "hairfastgan_b200.encoders"
         seg = importlib.import_module("models.CtrlHair.external_code.face_parsing.model")     # my_parsing_util.py:15
         assert seg.BiSeNet.__module__ == "hairfastgan_b200.bisenet"
+        bic = importlib.import_module("utils.bicubic")                                          # Embedding.py:13
+        assert bic.BicubicDownSample.__module__ == "hairfastgan_b200.bicubic"
         ns = {}
         exec("from nets.feature_style_encoder import *", ns)          # trainer.py:20
         assert ns["fs_encoder_v2"].__module__ == "hairfastgan_b200.encoders"

@@ -1,0 +1,52 @@
+"""Stage glue: BicubicDownSample.  CPU: oracle vs the reference golden, taps of the drop-in module;
+GPU: the fused kernel vs golden and oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import glue_oracle as GO
+
+torch.set_grad_enabled(False)
+
+
+def test_bicubic_oracle_and_taps(golden_dir):
+    import hairfastgan_b200.bicubic as B
+    g = np.load(os.path.join(golden_dir, "glue.npz"))
+    x = torch.from_numpy(g["x"])
+    for f in (2, 4):
+        assert float((GO.bicubic_downsample_ref(x, f) - torch.from_numpy(g[f"y_f{f}"])).abs().max()) < 1e-6
+        assert torch.equal(B.BicubicDownSample(factor=f).k, torch.from_numpy(g[f"k_f{f}"]))   # same taps, bit for bit
+        assert torch.equal(GO.bicubic_taps(f), torch.from_numpy(g[f"k_f{f}"]))
+    y = GO.bicubic_downsample_ref((x + 1) * 127.5, 4, clip_round=True)
+    assert float((y - torch.from_numpy(g["y_f4_clip_round"])).abs().max()) == 0.0
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        B.BicubicDownSample(factor=4)(x)
+    with pytest.raises(NotImplementedError):
+        B.BicubicDownSample(factor=4, padding="zeros")
+
+
+@pytest.mark.gpu
+def test_bicubic_downsample_gpu(golden_dir):
+    import hairfastgan_b200.bicubic as B
+    g = np.load(os.path.join(golden_dir, "glue.npz"))
+    x = torch.from_numpy(g["x"])
+    for f in (2, 4):
+        y = B.BicubicDownSample(factor=f)(x.cuda()).cpu()
+        assert y.shape == g[f"y_f{f}"].shape
+        assert float((y - torch.from_numpy(g[f"y_f{f}"])).abs().max()) < 2e-6
+    y = B.BicubicDownSample(factor=4)((x.cuda() + 1) * 127.5, clip_round=True).cpu()
+    assert float((y - torch.from_numpy(g["y_f4_clip_round"])).abs().max()) <= 1.0      # a .5 tie may round either way
+    assert float((y != torch.from_numpy(g["y_f4_clip_round"])).float().mean()) < 1e-3
+    yb = B.BicubicDownSample(factor=4)((x.cuda() + 1) * 127.5, nhwc=False, clip_round=True, byte_output=True)
+    assert yb.dtype == torch.uint8 and not yb.is_cuda
+    # the swap() shapes: 1024^2 -> 512^2 / 256^2, three images, against the oracle
+    big = torch.rand(3, 3, 1024, 1024, generator=torch.Generator().manual_seed(62)) * 2 - 1
+    for f in (2, 4):
+        y = B.BicubicDownSample(factor=f)(big.cuda()).cpu()
+        assert float((y - GO.bicubic_downsample_ref(big, f)).abs().max()) < 2e-6
+    xn = big[:1, :, :64, :96].permute(0, 2, 3, 1).contiguous()
+    yn = B.BicubicDownSample(factor=2)(xn.cuda(), nhwc=True).cpu()
+    assert yn.shape == (1, 32, 48, 3)
+    assert float((yn.permute(0, 3, 1, 2) - GO.bicubic_downsample_ref(big[:1, :, :64, :96], 2)).abs().max()) < 2e-6
