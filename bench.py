@@ -165,13 +165,16 @@ def run_ours(args, rank, world, local_rank):
     host_out = torch.empty(T, 3, 1024, 1024).pin_memory()
     launches = [0]
 
-    def compute(img, lats, lins):
+    def compute(img, lats, lins, skip_fse_recon=False):
         """The hot path of T triples through the public module API (what swap()'s stages call)."""
         n0 = lib.hf_total_launch_count()
         for net, x in ((e4e, img[0]), (e4e, img[1]), (fse, img[2])):   # Embedding.py:71,74 / :51
             net(x)
         final = None
         for i, (s, e, b, r) in enumerate(calls):
+            if i == 0 and skip_fse_recon:              # opt-in 8f-2 fast path: same RNG draws, no reconstruction
+                gen.consume_noise(b)
+                continue
             out = gen([lats[i]], input_is_latent=True, start_layer=s, end_layer=e, layer_in=lins[i])   # random noise
             if i == len(calls) - 1:
                 final = out[0]
@@ -294,6 +297,12 @@ def run_ours(args, rank, world, local_rank):
                 e0.record(); fn(); e1.record(); e1.synchronize()
                 tot += e0.elapsed_time(e1)
             return tot / n
+        # opt-in SURVEY 8f-2 fast path (install(skip_fse_reconstruction=True)): the step without the FSE reconstruction
+        # forward that swap() discards (445.6 GFLOP/triple), the noise still drawn
+        ms_skip = avg_ms(lambda: compute(dev_img, dev_lat, dev_lin, skip_fse_recon=True))
+        extra["fse_recon_skipped"] = {"value": round(T / (ms_skip * 1e-3), 3), "unit": "triples/s",
+                                      "ms_per_step": round(ms_skip, 3),
+                                      "note": "same outputs for swap(); not the default, see INTEGRATION.md"}
         # configs[1]: full 1024^2 generator forward, B=4
         lat4 = torch.randn(4, 18, 512, device=dev)
         us_img = avg_ms(lambda: gen([lat4], input_is_latent=True)) / 4 * 1e3

@@ -72,9 +72,19 @@ _POSTPROCESS = {
     "models.Encoders": ("FeatureEncoderMult", "FeatureiResnet"),
 }
 _saved_attrs = []
+# FeatureStyleEncoder/FSencoder.py:12-19 puts its directory on sys.path and does `from trainer import *`; with
+# install(skip_fse_reconstruction=True) Trainer.test gets the fast path of hairfastgan_b200/fse_fast.py
+_FSE_TRAINER = "trainer"
+_post_import = set()          # module names the meta-path hook currently patches
+_patched_trainers = []
 
 
 def _patch_postprocess(module) -> None:
+    if module.__name__ == _FSE_TRAINER:
+        fast = importlib.import_module("hairfastgan_b200.fse_fast")
+        if fast.patch_trainer_module(module):
+            _patched_trainers.append(module)
+        return
     ours = importlib.import_module("hairfastgan_b200.postprocess")
     for attr in _POSTPROCESS.get(module.__name__, ()):
         if hasattr(module, attr) and getattr(module, attr) is not getattr(ours, attr):
@@ -99,7 +109,7 @@ class _PostImportPatcher(importlib.abc.MetaPathFinder):
     _busy = False
 
     def find_spec(self, fullname, path=None, target=None):
-        if fullname not in _POSTPROCESS or _PostImportPatcher._busy:
+        if fullname not in _post_import or _PostImportPatcher._busy:
             return None
         _PostImportPatcher._busy = True
         try:
@@ -130,7 +140,7 @@ def _register(ref_name: str, ours: str) -> None:
 
 
 def install(generator: bool = True, encoders: bool = True, postprocess: bool = True, segmentation: bool = True,
-            glue: bool = True) -> None:
+            glue: bool = True, skip_fse_reconstruction: bool = False) -> None:
     """Register the overlay.  ``generator=False`` swaps only the operator package (L1 boundary) and leaves the
     reference's own ``models/stylegan2/model.py`` classes in place on top of our ops; ``encoders=False`` keeps
     the reference's PyTorch encoders; ``postprocess=False`` keeps its PostProcess conv stack; ``segmentation=False``
@@ -150,9 +160,15 @@ def install(generator: bool = True, encoders: bool = True, postprocess: bool = T
         for ref_name, ours in _ENCODERS.items():
             _register(ref_name, ours)
     if postprocess:
+        _post_import.update(_POSTPROCESS)
+    if skip_fse_reconstruction:
+        # opt-in: Trainer.test(img=..., return_latent=True) skips the StyleGAN reconstruction whose image swap() never
+        # reads (x_1_recon comes back as None) and draws the same noise, so later random numbers are unchanged
+        _post_import.add(_FSE_TRAINER)
+    if _post_import:
         if _patcher not in sys.meta_path:
             sys.meta_path.insert(0, _patcher)
-        for name in _POSTPROCESS:                    # already imported: rebind now
+        for name in list(_post_import):              # already imported: rebind now
             if name in sys.modules:
                 _patch_postprocess(sys.modules[name])
 
@@ -166,3 +182,7 @@ def uninstall() -> None:
     for module, attr, value in reversed(_saved_attrs):
         setattr(module, attr, value)
     _saved_attrs.clear()
+    for module in _patched_trainers:
+        importlib.import_module("hairfastgan_b200.fse_fast").unpatch_trainer_module(module)
+    _patched_trainers.clear()
+    _post_import.clear()

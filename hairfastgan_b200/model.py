@@ -423,6 +423,17 @@ class Generator(nn.Module):
         return ws
 
     # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def consume_noise(self, batch: int, device=None) -> None:
+        """Advance the RNG exactly as a full ``forward(..., noise=None, randomize_noise=True)`` of ``batch`` samples
+        would (one ``normal_()`` of shape [batch,1,R,R] per StyledConv, in execution order -- NoiseInjection.forward,
+        model.py:288-291) without running the network.  Used by the opt-in FSE fast path (`fse_fast.py`) that skips
+        the reconstruction image nobody reads while keeping every later random draw of ``swap()`` unchanged."""
+        dev = self.input.input.device if device is None else device
+        for i in range(self.num_layers):
+            r = 4 if i == 0 else 2 ** ((i + 1) // 2 + 2)
+            torch.empty(batch, 1, r, r, device=dev, dtype=torch.float32).normal_()
+
     def forward(self, styles, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
                 input_is_latent=False, noise=None, randomize_noise=True, layer_in=None, skip=None,
                 start_layer=0, end_layer=8, return_rgb=False):

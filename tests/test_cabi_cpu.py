@@ -160,6 +160,60 @@ def test_install_rebinds_postprocess_classes(tmp_path):
         sys.modules.update(saved)
 
 
+def test_fse_reconstruction_skip_is_opt_in_and_results_identical(tmp_path):
+    """install(skip_fse_reconstruction=True) rebinds Trainer.test of the FeatureStyleEncoder `trainer`
+    module; the fast path returns the same (w_recon, fea), None for the unused image, and asks the generator for the
+    RNG draws of the skipped forward.  A stand-in trainer module plays the reference here."""
+    import sys
+    import hairfastgan_b200.install as inst
+    (tmp_path / "trainer.py").write_text(
+        "class Trainer:\n"
+        "    def test(self, w=None, img=None, noise=None, zero_noise_input=True, return_latent=False, training_mode=False):\n"
+        "        return ['original', return_latent]\n")
+    saved = sys.modules.pop("trainer", None)
+    sys.path.insert(0, str(tmp_path))
+    try:
+        inst.install()                                   # default: not patched
+        import importlib
+        mod = importlib.import_module("trainer")
+        assert not hasattr(mod.Trainer.test, "__wrapped__")
+        inst.uninstall()
+        inst.install(skip_fse_reconstruction=True)       # already imported: patched in place
+        assert hasattr(mod.Trainer.test, "__wrapped__")
+
+        class Gen:
+            drawn = []
+
+            def consume_noise(self, batch, device=None):
+                self.drawn.append(batch)
+
+        t = mod.Trainer()
+        t.config, t.scale, t.scale_mode = {"use_fs_encoder": True}, 1, "bilinear"
+        t.dlatent_avg = torch.ones(18, 512)
+        t.enc = lambda x: (torch.full((x.shape[0], 18, 512), 2.0), x.mean((2, 3)))
+        t.StyleGAN = Gen()
+        img = torch.rand(3, 4, 16, 16)
+        out = t.test(img=img, return_latent=True)
+        assert out[1] is None and torch.equal(out[0], img[:, :3]) and torch.equal(out[2], torch.full((3, 18, 512), 3.0))
+        assert torch.allclose(out[3], F_interp_mean(img)) and Gen.drawn == [3] and t.n_iter == 1e5
+        assert t.test(img=img, return_latent=False) == ["original", False]         # every other call: the reference
+        t.StyleGAN = object()                                                       # not our generator: the reference
+        assert t.test(img=img, return_latent=True) == ["original", True]
+        inst.uninstall()
+        assert not hasattr(mod.Trainer.test, "__wrapped__")
+    finally:
+        inst.uninstall()
+        sys.path.remove(str(tmp_path))
+        sys.modules.pop("trainer", None)
+        if saved is not None:
+            sys.modules["trainer"] = saved
+
+
+def F_interp_mean(img):
+    import torch.nn.functional as F
+    return F.interpolate(img, scale_factor=0.5, mode="bilinear").mean((2, 3))
+
+
 def test_conv_plans_for_every_generator_layer(lib):
     """Tiling decisions for the 17 StyledConvs of the 1024^2 generator (no device needed): shared memory
     fits the 227 KB opt-in limit, 4^2/8^2 use the per-tap kernel, everything else the halo kernel, the three

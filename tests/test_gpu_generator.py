@@ -164,3 +164,21 @@ def test_fse_generator_variant_golden(M, golden_dir):
     assert none is None
     with pytest.raises(RuntimeError, match="feature_scale == 1.0"):
         gen([lat], input_is_latent=True, noise=noise, features_in=[None] * 5 + [fea] + [None] * 12, feature_scale=0.5)
+
+
+def test_consume_noise_advances_rng_like_a_forward():
+    """The opt-in FSE fast path (fse_fast.py) skips a full forward but must leave the random stream
+    where the reference would: consume_noise() == the draws of forward(randomize_noise=True)."""
+    import hairfastgan_b200.fse_model as FM
+    torch.manual_seed(0)
+    gen = FM.Generator(256, 512, 8).cuda().eval()
+    lat = torch.randn(3, gen.n_latent, 512, device="cuda")
+    torch.manual_seed(123)
+    gen([lat], input_is_latent=True, return_features=True)             # random noise, like Trainer.get_image
+    after_forward = torch.randn(1000, device="cuda")
+    torch.manual_seed(123)
+    gen.consume_noise(3)
+    after_skip = torch.randn(1000, device="cuda")
+    assert torch.equal(after_forward, after_skip)
+    torch.manual_seed(123)                                              # control: without the draws the stream differs
+    assert not torch.equal(after_forward, torch.randn(1000, device="cuda"))
