@@ -510,6 +510,8 @@ def main():
                    "l2": "256 MiB flush write between timed steps; value: per-step CUDA events summed; e2e: one event "
                          "pair around all steps, uploads/downloads double-buffered on side streams"},
         "tflops_algorithmic": round(GFLOP_PER_TRIPLE * value / 1e3, 1),
+        # whole-step fraction of the conv roofline: algorithmic FLOP/s over all GPUs / (N x measured bf16 peak)
+        "frac_of_tensor_peak": round(GFLOP_PER_TRIPLE * value / 1e3 / (world * peaks()["tf_burst"]), 4),
         "e2e": {"value": round(e2e_value, 3), "unit": "triples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": T * 3 * 1024 * 1024 * 4},
         "gpu_launches": n_launch, "clocks": clocks,
