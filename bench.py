@@ -285,7 +285,10 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop(first) if rank == 0 else None
 
     extra = {"nccl_broadcast_bytes_at_init": bcast_bytes}
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and args.no_extras:
+        extra["roofline"] = roofline
+        extra["roofline_b4"] = roofline_b4
+    elif rank == 0 and world == 1:
         def avg_ms(fn, n=5):
             for _ in range(3):
                 fn()
@@ -457,6 +460,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--triples", type=int, default=16, help="independent triples batched per step and GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-network / per-operator side measurements")
     ap.add_argument("--profile-step", action="store_true", help="run one step between cudaProfilerStart/Stop, no JSON")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
