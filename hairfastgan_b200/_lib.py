@@ -123,6 +123,8 @@ SYMBOLS = {
                                                 C.c_int, C.c_int, C.c_void_p]),
     "hf_bicubic_downsample_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_int, C.c_void_p]),
+    "hf_dilate_erode_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_void_p]),
     "hf_generator_packed_bytes": (C.c_size_t, [C.POINTER(hf_gen_config)]),
     "hf_generator_workspace_bytes": (C.c_size_t, [C.POINTER(hf_gen_config), C.c_int]),
     "hf_generator_pack": (C.c_int, [C.POINTER(hf_gen_config), C.POINTER(hf_gen_weights), C.c_void_p, C.c_void_p]),

@@ -162,6 +162,14 @@ int hf_bicubic_downsample_f32(const float* x, const float* kernel, float* y, int
   return launch_bicubic_down(x, kernel, y, planes, height, width, factor, clip_round, (cudaStream_t)stream);
 }
 
+int hf_dilate_erode_f32(const float* mask, float* dilate, float* erode, void* workspace, int planes, int height,
+                        int width, int iterations, void* stream) {
+  int rc = ensure_device_current();
+  if (rc) return rc;
+  return launch_dilate_erode(mask, dilate, erode, (float*)workspace, planes, height, width, iterations,
+                             (cudaStream_t)stream);
+}
+
 int hf_bilinear_upsample_nchw_f32(const float* x, float* y, int batch, int channels, int in_channels, int h, int w,
                                   int height, int width, void* stream) {
   int rc = ensure_device_current();

@@ -74,4 +74,58 @@ int launch_bicubic_down(const float* x, const float* k, float* y, int planes, in
   return HF_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// DilateErosion.mask (utils/image_utils.py:42-55): `iterations` rounds of a 3x3 cross "convolution" with zero padding
+// followed by a threshold -- dilation keeps sum > 0, erosion keeps sum == 5.  One launch per round, both masks at
+// once, ping-pong between two caller-provided planes; the arithmetic is on exact small integers in fp32.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dilate_erode_step_kernel(const float* __restrict__ din,
+                                                                const float* __restrict__ ein,
+                                                                float* __restrict__ dout, float* __restrict__ eout,
+                                                                int H, int W, int total) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int x = i % W, t = i / W, y = t % H;
+    const float* dp = din + i;
+    const float* ep = ein + i;
+    float sd = __ldg(dp), se = __ldg(ep);                          // centre, up, down, left, right
+    if (y > 0) { sd += __ldg(dp - W); se += __ldg(ep - W); }
+    if (y + 1 < H) { sd += __ldg(dp + W); se += __ldg(ep + W); }
+    if (x > 0) { sd += __ldg(dp - 1); se += __ldg(ep - 1); }
+    if (x + 1 < W) { sd += __ldg(dp + 1); se += __ldg(ep + 1); }
+    dout[i] = sd > 0.f ? 1.f : 0.f;
+    eout[i] = se == 5.f ? 1.f : 0.f;
+  }
+}
+
+int launch_dilate_erode(const float* mask, float* dilate, float* erode, float* ws, int planes, int H, int W,
+                        int iterations, cudaStream_t st) {
+  HF_REQUIRE(mask && dilate && erode, "dilate_erode: null pointer");
+  HF_REQUIRE(planes > 0 && H > 0 && W > 0 && iterations >= 0, "dilate_erode: bad arguments");
+  const int64_t total = (int64_t)planes * H * W;
+  HF_REQUIRE(total < (int64_t)2000000000, "dilate_erode: tensor too large for one launch");
+  const size_t bytes = (size_t)total * sizeof(float);
+  if (iterations == 0) {
+    HF_CUDA_OK(cudaMemcpyAsync(dilate, mask, bytes, cudaMemcpyDeviceToDevice, st));
+    HF_CUDA_OK(cudaMemcpyAsync(erode, mask, bytes, cudaMemcpyDeviceToDevice, st));
+    return HF_OK;
+  }
+  HF_REQUIRE(iterations == 1 || ws, "dilate_erode: workspace (2 planes sets) needed for more than one iteration");
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
+  // buffers: round r reads (d_in, e_in) and writes (d_out, e_out); the last round writes the outputs
+  const float *d_in = mask, *e_in = mask;
+  float* tmp_d[2] = {ws, ws ? ws + 2 * total : nullptr};
+  float* tmp_e[2] = {ws ? ws + total : nullptr, ws ? ws + 3 * total : nullptr};
+  for (int r = 0; r < iterations; ++r) {
+    const bool last = r == iterations - 1;
+    float* d_out = last ? dilate : tmp_d[r & 1];
+    float* e_out = last ? erode : tmp_e[r & 1];
+    dilate_erode_step_kernel<<<grid, 256, 0, st>>>(d_in, e_in, d_out, e_out, H, W, (int)total);
+    HF_LAUNCH_OK("dilate_erode_step");
+    count_launch();
+    d_in = d_out; e_in = e_out;
+  }
+  return HF_OK;
+}
+
 }  // namespace hf

@@ -69,6 +69,8 @@ int launch_gate_add_up(const void* x16, const float* gate, const float* addvec, 
                        int h, int w, int C, int up, int dtype, cudaStream_t st);
 int launch_bicubic_down(const float* x, const float* k, float* y, int planes, int H, int W, int factor, int clip_round,
                         cudaStream_t st);
+int launch_dilate_erode(const float* mask, float* dilate, float* erode, float* ws, int planes, int H, int W,
+                        int iterations, cudaStream_t st);
 int launch_bilinear_up_nchw(const float* x, float* y, int B, int C, int Cin, int h, int w, int H, int W,
                             cudaStream_t st);
 int launch_se_gate(const void* x16, const float* fc1, const float* fc2, float* out, float* ws, int B, int HW, int C,

@@ -26,6 +26,8 @@ After ``install()`` the import statements of the reference resolve to this packa
 
 * ``from utils.bicubic import BicubicDownSample`` (models/Embedding.py:13, models/Blending.py:6)
                                                                                     -> ``hairfastgan_b200.bicubic``
+* ``from utils.image_utils import DilateErosion`` (models/Alignment.py:11, models/Blending.py:7): the name is rebound
+  inside ``utils.image_utils`` after import                                         -> ``hairfastgan_b200.masks``
 
 Nothing in the reference tree is edited and its JIT build of the two 2019 CUDA extensions
 (op/fused_act.py:10-16, op/upfirdn2d.py:10-16) never runs.
@@ -71,6 +73,10 @@ _POSTPROCESS = {
     "models.Net": ("FeatureEncoder", "FeatureEncoderMult"),
     "models.Encoders": ("FeatureEncoderMult", "FeatureiResnet"),
 }
+# stage glue living in a module with unrelated content: utils/image_utils.py also holds the Poisson-blending helpers
+_GLUE_ATTRS = {
+    "utils.image_utils": (("DilateErosion", "hairfastgan_b200.masks"),),
+}
 _saved_attrs = []
 # FeatureStyleEncoder/FSencoder.py:12-19 puts its directory on sys.path and does `from trainer import *`; with
 # install(skip_fse_reconstruction=True) Trainer.test gets the fast path of hairfastgan_b200/fse_fast.py
@@ -85,8 +91,10 @@ def _patch_postprocess(module) -> None:
         if fast.patch_trainer_module(module):
             _patched_trainers.append(module)
         return
-    ours = importlib.import_module("hairfastgan_b200.postprocess")
-    for attr in _POSTPROCESS.get(module.__name__, ()):
+    rebind = [(attr, "hairfastgan_b200.postprocess") for attr in _POSTPROCESS.get(module.__name__, ())]
+    rebind += list(_GLUE_ATTRS.get(module.__name__, ()))
+    for attr, ours_name in rebind:
+        ours = importlib.import_module(ours_name)
         if hasattr(module, attr) and getattr(module, attr) is not getattr(ours, attr):
             _saved_attrs.append((module, attr, getattr(module, attr)))
             setattr(module, attr, getattr(ours, attr))
@@ -161,6 +169,8 @@ def install(generator: bool = True, encoders: bool = True, postprocess: bool = T
             _register(ref_name, ours)
     if postprocess:
         _post_import.update(_POSTPROCESS)
+    if glue:
+        _post_import.update(_GLUE_ATTRS)
     if skip_fse_reconstruction:
         # opt-in: Trainer.test(img=..., return_latent=True) skips the StyleGAN reconstruction whose image swap() never
         # reads (x_1_recon comes back as None) and draws the same noise, so later random numbers are unchanged

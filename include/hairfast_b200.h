@@ -291,6 +291,12 @@ int hf_bilinear_upsample_nchw_f32(const float* x, float* y, int batch, int chann
 int hf_bicubic_downsample_f32(const float* x, const float* kernel, float* y, int planes, int height, int width,
                               int factor, int clip_round, void* stream);
 
+/* DilateErosion.mask (utils/image_utils.py:42-55): `iterations` rounds of {3x3 cross sum with zero padding; dilation
+ * keeps sum > 0, erosion keeps sum == 5}, both started from `mask` [planes,H,W] fp32 (values 0 / 1).
+ * workspace: 4 * planes * H * W floats (unused when iterations <= 1). */
+int hf_dilate_erode_f32(const float* mask, float* dilate, float* erode, void* workspace, int planes, int height,
+                        int width, int iterations, void* stream);
+
 /* Number of kernels the last hf_generator_forward / hf_conv_forward of this thread launched. */
 int hf_last_launch_count(void);
 /* Number of kernels every hf_* call of this thread has launched since the library was loaded. */

@@ -9,6 +9,22 @@ from __future__ import annotations
 import torch
 
 
+def _cross_sum(m: torch.Tensor) -> torch.Tensor:
+    """Sum over the 5-point cross with zero padding (the reference's conv2d with a 3x3 cross weight, padding='same')."""
+    p = torch.nn.functional.pad(m, (1, 1, 1, 1))
+    return p[..., 1:-1, 1:-1] + p[..., :-2, 1:-1] + p[..., 2:, 1:-1] + p[..., 1:-1, :-2] + p[..., 1:-1, 2:]
+
+
+def dilate_erode_ref(mask: torch.Tensor, iterations: int):
+    """``DilateErosion.mask`` (utils/image_utils.py:42-55): `iterations` rounds of cross sum + threshold (> 0 for the
+    dilated copy, == 5 for the eroded copy), both starting from ``mask`` [N,1,H,W]."""
+    grown, shrunk = mask.float().clone(), mask.float().clone()
+    for _ in range(iterations):
+        grown = (_cross_sum(grown) > 0).float()
+        shrunk = (_cross_sum(shrunk) == 5.0).float()
+    return grown, shrunk
+
+
 def bicubic_taps(factor: int, a: float = -0.5) -> torch.Tensor:
     """utils/bicubic.py:7-25: Keys kernel sampled at (i - floor(2f) + 0.5) / f, i < 4f, normalised to sum 1."""
     size = 4 * factor

@@ -160,6 +160,34 @@ def test_install_rebinds_postprocess_classes(tmp_path):
         sys.modules.update(saved)
 
 
+def test_install_rebinds_dilate_erosion(tmp_path):
+    """utils/image_utils.py stays the reference's module (Poisson blending helpers, ...); only DilateErosion is
+    rebound after import (a stand-in package plays the reference)."""
+    import sys
+    import hairfastgan_b200.install as inst
+    import hairfastgan_b200.masks as MK
+    pkg = tmp_path / "utils"
+    pkg.mkdir()
+    (pkg / "__init__.py").write_text("")
+    (pkg / "image_utils.py").write_text("class DilateErosion: pass\ndef poisson_image_blending(): return 'reference'\n")
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "utils" or k.startswith("utils.")}
+    sys.path.insert(0, str(tmp_path))
+    try:
+        inst.install()
+        import importlib
+        iu = importlib.import_module("utils.image_utils")
+        assert iu.DilateErosion is MK.DilateErosion and iu.poisson_image_blending() == "reference"
+        assert importlib.import_module("utils.bicubic").BicubicDownSample.__module__ == "hairfastgan_b200.bicubic"
+        inst.uninstall()
+        assert iu.DilateErosion.__module__ == "utils.image_utils"
+    finally:
+        inst.uninstall()
+        sys.path.remove(str(tmp_path))
+        for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
 def test_fse_reconstruction_skip_is_opt_in_and_results_identical(tmp_path):
     """install(skip_fse_reconstruction=True) rebinds Trainer.test of the FeatureStyleEncoder `trainer`
     module; the fast path returns the same (w_recon, fea), None for the unused image, and asks the generator for the

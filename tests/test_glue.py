@@ -27,6 +27,40 @@ def test_bicubic_oracle_and_taps(golden_dir):
         B.BicubicDownSample(factor=4, padding="zeros")
 
 
+def test_dilate_erode_oracle(golden_dir):
+    g = np.load(os.path.join(golden_dir, "glue.npz"))
+    m = torch.from_numpy(g["mask_in"]).float()
+    for it in (1, 5):
+        d, e = GO.dilate_erode_ref(m, it)
+        assert torch.equal(d, torch.from_numpy(g[f"dilate_it{it}"]).float())      # integer work: bit-exact
+        assert torch.equal(e, torch.from_numpy(g[f"erode_it{it}"]).float())
+    d0, e0 = GO.dilate_erode_ref(m, 0)
+    assert torch.equal(d0, m) and torch.equal(e0, m)
+
+
+@pytest.mark.gpu
+def test_dilate_erosion_gpu(golden_dir):
+    import hairfastgan_b200.masks as MK
+    g = np.load(os.path.join(golden_dir, "glue.npz"))
+    m = torch.from_numpy(g["mask_in"]).float()
+    for it in (1, 5):
+        d, e = MK.DilateErosion(dilate_erosion=it).mask(m.cuda())
+        assert torch.equal(d.cpu(), torch.from_numpy(g[f"dilate_it{it}"]).float())
+        assert torch.equal(e.cpu(), torch.from_numpy(g[f"erode_it{it}"]).float())
+    d0, e0 = MK.DilateErosion(dilate_erosion=0).mask(m.cuda())
+    assert torch.equal(d0.cpu(), m) and torch.equal(e0.cpu(), m)
+    labels = torch.from_numpy(g["labels"]).float()
+    d, e = MK.DilateErosion(dilate_erosion=2).hair_from_mask(labels.cuda())
+    assert torch.equal(d.cpu(), torch.from_numpy(g["hair_dilate"]).float())
+    assert torch.equal(e.cpu(), torch.from_numpy(g["hair_erode"]).float())
+    big = (torch.rand(8, 1, 256, 256, generator=torch.Generator().manual_seed(64)) > 0.7).float()   # swap() size
+    d, e = MK.DilateErosion(dilate_erosion=5).mask(big.cuda())
+    do, eo = GO.dilate_erode_ref(big, 5)
+    assert torch.equal(d.cpu(), do) and torch.equal(e.cpu(), eo)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        MK.DilateErosion(dilate_erosion=5, device="cpu").mask(big)
+
+
 @pytest.mark.gpu
 def test_bicubic_downsample_gpu(golden_dir):
     import hairfastgan_b200.bicubic as B
