@@ -13,7 +13,13 @@
 // channel chunks; operands in swizzled K-major shared memory, tcgen05.mma kind::f16 with fp32
 // accumulators in TMEM, persistent CTAs with a static schedule, two accumulator buffers.
 //
-// Two kernels share the epilogue:
+// The same kernels run the plain convolutions of the encoders / PostProcess stack / BiSeNet (`epi == 1`:
+// v = act(acc*scale[o] + shift[o]) (+ residual, before or after the activation), optional second output
+// v*s2[o] + b2[o] for the next block's BatchNorm; stride 2 through TMA element strides; grouped heads).
+//
+// Three kernels share the epilogues:
+//  * conv_halo2_kernel (cluster of 2, cta_group::2): the halo scheme below for N tile 256 with streamed weights;
+//    each CTA owns its own pixel tile and half of the weight tile, the leader issues M = 256 MMAs for the pair.
 //  * conv_halo_kernel (H % 16 == 0, W % 8 == 0): per 64-channel chunk ONE TMA 4-D box brings the
 //    (16+2) x (8+2)-pixel halo of an 8x16-pixel tile into a ring slot; the nine taps are nine UMMA
 //    descriptors that start (dy*pitch + dx) rows into that slot with SBO = one halo row (measured on
@@ -23,10 +29,10 @@
 //    one 256-column accumulator buffer (G * n_tile <= 256), so narrow layers amortise every barrier /
 //    commit over the same amount of work as a wide one, and each weight tile is reused by G tiles.
 //    Weights either stay RESIDENT in smem for the whole kernel (single channel chunk, single N tile) or
-//    stream through their own TMA ring.  Two 4-warp epilogue groups alternate rounds.
-//  * conv_igemm_kernel (any shape; used for 4^2 / 8^2): one TMA box per (tap, chunk) shifted by the tap
-//    offset; the 128 GEMM rows may span several batch samples (4x4x8, 8x8x2).
-// In both, TMA out-of-bounds zero fill *is* the conv zero padding.
+//    stream through their own TMA ring.  NG (2 or 4) 4-warp epilogue groups alternate rounds, one TMEM buffer each.
+//  * conv_igemm_kernel (any shape; used for 4^2 / 8^2, stride 2, 1x1, grouped): one TMA box per (tap, chunk)
+//    shifted by the tap offset; the 128 GEMM rows may span several batch samples (4x4x8, 8x8x2).
+// In all of them TMA out-of-bounds zero fill *is* the conv zero padding.
 #include <stdlib.h>
 #include <string.h>
 
