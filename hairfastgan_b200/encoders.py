@@ -10,8 +10,9 @@ checkpoints load unchanged):
 
 The nn.Modules below only own parameters; ``forward`` runs NHWC 16-bit activations through
 ``hf_conv2d_forward`` (tcgen05 implicit GEMM; eval-mode BatchNorm folded into weights / epilogue, PReLU /
-LeakyReLU / residual add fused) plus a few HBM-bound glue kernels (``nn16``).  The tiny dense layers
-(SE excitation MLP, EqualLinear / nn.Linear style heads) are plain cuBLAS GEMMs through torch.
+LeakyReLU / residual add fused) plus a few HBM-bound glue kernels (``nn16``: SE pooling + gate, SE combine,
+FPN upsample-add, adaptive pooling).  The small dense style heads (EqualLinear / nn.Linear) are plain cuBLAS GEMMs
+through torch.
 Eval mode only (running statistics); CUDA only, no fallback.
 """
 from __future__ import annotations
@@ -21,7 +22,6 @@ from collections import namedtuple
 
 import torch
 from torch import nn
-from torch.nn import functional as F
 
 from . import nn16
 from .model import EqualLinear

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import stylegan2_oracle as O
-from tests.gpu_util import TOL_FP32, TOL_SINGLE, dtype_name, record, rel_err
+from tests.gpu_util import TOL_SINGLE, dtype_name, record, rel_err
 
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)

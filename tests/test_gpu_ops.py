@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import stylegan2_oracle as O
-from tests.gpu_util import TOL_FP32, record
+from tests.gpu_util import TOL_FP32
 
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)

@@ -2,7 +2,6 @@
 every conv / rgb_combine launch with CUDA events and print them).  Usage: python tools/prof_chain.py [B]"""
 import os
 import sys
-import time
 
 os.environ.setdefault("HF_GEN_PROFILE", "1")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
