@@ -110,6 +110,10 @@ class _PatchingLoader(importlib.abc.Loader):
     def exec_module(self, module):
         self.inner.exec_module(module)
         _patch_postprocess(module)
+        for name in list(_post_import):          # targets pulled in as a side effect while the hook was re-entrant
+            other = sys.modules.get(name)
+            if other is not None and other is not module:
+                _patch_postprocess(other)
 
 
 class _PostImportPatcher(importlib.abc.MetaPathFinder):
