@@ -54,10 +54,21 @@ __global__ void __launch_bounds__(256) im2col7x7s2_kernel(const float* __restric
     const float* xb = x + (size_t)b * 3 * plane;
     const int ybase = 2 * oy - 3, xbase = 2 * ox0 - 3;
     __syncthreads();
-    for (int i = threadIdx.x; i < 21 * SW; i += blockDim.x) {
+    // two unrolled phases: every global load of a thread is in flight before its first shared store
+    constexpr int N_STAGE = (21 * SW + 255) / 256;
+    float stage[N_STAGE];
+#pragma unroll
+    for (int it = 0; it < N_STAGE; ++it) {
+      const int i = threadIdx.x + it * 256;
       const int rr = i / SW, q = i - rr * SW;
       const int c = rr / 7, yy = ybase + (rr - c * 7), xx = xbase + q;
-      sx[rr][q] = ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) ? __ldg(xb + c * plane + yy * W + xx) : 0.f;
+      stage[it] = (i < 21 * SW && (unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W)
+                      ? __ldg(xb + c * plane + yy * W + xx) : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < N_STAGE; ++it) {
+      const int i = threadIdx.x + it * 256;
+      if (i < 21 * SW) sx[i / SW][i - (i / SW) * SW] = stage[it];
     }
     __syncthreads();
     const int npix = min(kI2cTile, Wo - ox0);
