@@ -1,0 +1,138 @@
+"""One process = one arm of the full `HairFast.swap()` comparison (BASELINE configs[2]).
+
+    python baseline/run_swap.py --mode reference|overlay|overlay_fast --work DIR --out result.pt [--reps N]
+
+* reference     the staged, unmodified checkout: cuDNN grouped convolutions + its two JIT kernels, fp32/TF32
+* overlay       the same checkout with hairfastgan_b200.install() active (this package's modules under its names)
+* overlay_fast  overlay + install(skip_fse_reconstruction=True) (hairfastgan_b200/fse_fast.py)
+
+Three synthetic images `torch.rand(3,1024,1024)` (seeds 0,1,2) are passed as tensors (hair_swap.py:63-105), synthetic
+checkpoints come from baseline/synth_checkpoints.py, `swap(..., seed=3407)` is the default seed (utils/seed.py:22-28).
+The result file holds the final image of every repetition, the Embedding-stage latents of the last one and the wall /
+CUDA-event timings: whole swap, and the share spent inside the hot-path modules (generator, e4e, FS encoder,
+PostProcess conv stack, BiSeNet) measured with forward hooks -- the hot-path / out-of-scope split of SURVEY 8d.
+Harness (tests/test_gpu_swap.py, bench.py's full-swap leg); not product code.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from baseline import refenv, synth_checkpoints  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", choices=["reference", "overlay", "overlay_fast"], required=True)
+    ap.add_argument("--work", default="/tmp/hairfast_work")
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--seed", type=int, default=None)
+    ap.add_argument("--same_shape_color", action="store_true", help="shape image is the color image (hair_swap.py:54)")
+    a = ap.parse_args()
+    work = os.path.abspath(a.work)
+
+    if not os.path.exists(os.path.join(work, "pretrained_models", ".complete_seed0")):
+        # the writer needs the STOCK classes: do it in a child so this process keeps a single mode
+        import subprocess
+        subprocess.run([sys.executable, os.path.join(HERE, "synth_checkpoints.py"), work], check=True)
+
+    refenv.activate(overlay=a.mode != "reference", skip_fse_reconstruction=a.mode == "overlay_fast", workdir=work)
+    import torch
+    assert torch.cuda.is_available(), "run_swap.py needs a GPU (tools/dryrun_swap_cpu.py is the CPU dry run)"
+    from hair_swap import HairFast, get_parser      # the reference's own hair_swap.py
+
+    t0 = time.time()
+    hair_fast = HairFast(get_parser().parse_args([]))
+    torch.cuda.synchronize()
+    init_s = time.time() - t0
+
+    # ---- hot-path accounting: CUDA events around the forward of every in-scope module ----------------------------
+    from models.CtrlHair.external_code.face_parsing.my_parsing_util import FaceParsing
+    hot = {
+        "generator": hair_fast.net.generator,
+        "fse_generator": hair_fast.embed.encoder.StyleGAN,
+        "e4e": hair_fast.embed.e4e.encoder,
+        "fse_encoder": hair_fast.embed.encoder.enc,
+        "pp_encoder": hair_fast.blend.post_process.encoder_face,
+        "pp_to_feature": hair_fast.blend.post_process.to_feature,
+        "bisenet": FaceParsing.bise_net,
+    }
+    spans = []
+
+    def pre(name):
+        def hook(m, inp):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            spans.append([name, ev, None])
+        return hook
+
+    def post(m, inp, out):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        for s in reversed(spans):
+            if s[2] is None:
+                s[2] = ev
+                break
+    for name, mod in hot.items():
+        mod.register_forward_pre_hook(pre(name))
+        mod.register_forward_hook(post)
+
+    imgs = [torch.rand(3, 1024, 1024, generator=torch.Generator().manual_seed(s)) for s in range(3)]
+    if a.same_shape_color:
+        imgs[2] = imgs[1]
+    kw = {} if a.seed is None else {"seed": a.seed}
+
+    # capture the Embedding-stage outputs of the last repetition (models/Embedding.py:93-101)
+    captured = {}
+    orig_embed = hair_fast.embed.embedding_images
+
+    def embedding_images(*args, **kwargs):
+        res = orig_embed(*args, **kwargs)
+        captured.clear()
+        for name, d in res.items():
+            for k, v in d.items():
+                captured[f"{name}.{k}"] = v.detach().float().cpu() if v.is_floating_point() else v.detach().cpu()
+        return res
+    hair_fast.embed.embedding_images = embedding_images
+
+    finals, timings = [], []
+    for rep in range(a.warmup + a.reps):
+        spans.clear()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record()
+        final = hair_fast.swap(*imgs, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.time() - w0) * 1e3
+        per = {}
+        for name, s, e in spans:
+            per[name] = per.get(name, 0.0) + s.elapsed_time(e)
+        hot_ms = sum(per.values())
+        if rep >= a.warmup:
+            finals.append(final.detach().float().cpu())
+            timings.append({"wall_ms": wall, "gpu_ms": e0.elapsed_time(e1), "hot_path_ms": hot_ms,
+                            "out_of_scope_ms": e0.elapsed_time(e1) - hot_ms, "per_module_ms": per,
+                            "hot_calls": len(spans)})
+    summary = {"mode": a.mode, "init_s": init_s, "timings": timings,
+               "final_shape": list(finals[-1].shape), "final_min": float(finals[-1].min()),
+               "final_max": float(finals[-1].max()), "finite": bool(torch.isfinite(finals[-1]).all()),
+               "deterministic": bool(all(torch.equal(finals[0], f) for f in finals[1:])),
+               "device": torch.cuda.get_device_name(0),
+               "dtype": os.environ.get("HAIRFAST_DTYPE", "bf16") if a.mode != "reference" else "fp32/tf32",
+               "generator_class": type(hair_fast.net.generator).__module__}
+    print(json.dumps(summary))
+    if a.out:
+        torch.save({"finals": finals, "embed": dict(captured), "summary": summary}, a.out)
+
+
+if __name__ == "__main__":
+    main()

@@ -898,10 +898,16 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 int conv_up_nc(int Cout) { return Cout < 32 ? Cout : 32; }
 
+// Experiment knobs (HF_CONV_V1: force the v1 kernel; HF_CONV_DBG: drop the epilogue -> WRONG outputs) exist only in
+// -DHF_DEBUG builds; the shipped library never reads the environment on the launch path.
+#ifdef HF_DEBUG
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
+#else
+static constexpr int env_int(const char*, int dflt) { return dflt; }
+#endif
 
 int conv_plan(const ConvLaunch& a, ConvPlan* p) {
   HF_REQUIRE(a.B > 0 && a.H > 0 && a.W > 0, "conv: bad shape B=%d H=%d W=%d", a.B, a.H, a.W);

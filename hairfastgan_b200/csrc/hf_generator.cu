@@ -183,6 +183,7 @@ int hf_generator_pack(const hf_gen_config* cfg, const hf_gen_weights* w, void* p
   GenLayout L;
   int rc = make_layout(cfg, &L);
   if (rc) return rc;
+  if ((rc = ensure_device_current())) return rc;
   HF_REQUIRE(w && packed, "hf_generator_pack: null pointer");
   HF_REQUIRE(((uintptr_t)packed & 255) == 0, "hf_generator_pack: packed buffer must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -226,6 +227,7 @@ int hf_generator_forward(const hf_gen_config* cfg, const void* packed, const hf_
   GenLayout L;
   int rc = make_layout(cfg, &L);
   if (rc) return rc;
+  if ((rc = ensure_device_current())) return rc;
   reset_launch_count();
   HF_REQUIRE(packed && io && workspace, "hf_generator_forward: null pointer");
   HF_REQUIRE(((uintptr_t)packed & 255) == 0 && ((uintptr_t)workspace & 255) == 0,

@@ -38,7 +38,9 @@ __global__ void __launch_bounds__(256) bicubic_down_kernel(const float* __restri
     const int oy = oy0 + r;
     float acc = 0.f;
     if (oy < Ho) {
-      const int xc = reflect_index(ix0 + c, W);
+      // columns right of the last valid output of a partial tile are never read back: clamp them into the plane
+      // (a single reflection of ix0 + c >= 2W - 1 would land before the row start)
+      const int xc = min(max(reflect_index(ix0 + c, W), 0), W - 1);
       const int iy0 = oy * f - p0;
       for (int t = 0; t < taps; ++t) acc = fmaf(kf[t], __ldg(xp + (size_t)reflect_index(iy0 + t, H) * W + xc), acc);
       if (clip_round) acc = fminf(fmaxf(rintf(acc), 0.f), 255.f);

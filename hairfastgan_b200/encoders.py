@@ -281,6 +281,33 @@ def _iresnet_layer(inplanes, planes, blocks, stride=2):
     return nn.Sequential(*layers)
 
 
+def _load_arcface_trunk(module, path):
+    """The reference does ``iresnet50().load_state_dict(torch.load(path))`` STRICTLY and then takes the trunk children
+    (nets/feature_style_encoder.py:16-17,27-33; models/Net.py:340-341).  Here the trunk lives under the encoder's own
+    names, so the keys are remapped -- and every trunk tensor of the module must be covered, every trunk key of the file
+    must be consumed (a renamed or missing key would otherwise leave random weights silently).  The iresnet head
+    (bn2 / fc / features), which the reference also loads and then drops, is the only part allowed to be unused."""
+    sd = torch.load(path, map_location="cpu", weights_only=True)
+    remap = {"conv1": "conv.0", "bn1": "conv.1", "prelu": "conv.2", "layer1": "block_1", "layer2": "block_2",
+             "layer3": "block_3", "layer4": "block_4"}
+    dropped_heads = ("bn2", "fc", "features", "dropout")
+    mine, unexpected = {}, []
+    for k, v in sd.items():
+        head = k.split(".")[0]
+        if head in remap:
+            mine[remap[head] + k[len(head):]] = v
+        elif head not in dropped_heads:
+            unexpected.append(k)
+    trunk = tuple(remap.values())
+    own = [k for k in module.state_dict() if k.startswith(tuple(t + "." for t in trunk))]
+    missing = [k for k in own if k not in mine]
+    extra = [k for k in mine if k not in own]
+    if missing or extra or unexpected:
+        raise RuntimeError(f"ArcFace checkpoint {path} does not match the iresnet50 trunk: missing {missing[:5]}, "
+                           f"unexpected {(extra + unexpected)[:5]}")
+    module.load_state_dict(mine, strict=False)
+
+
 class fs_encoder_v2(nn.Module):
     def __init__(self, n_styles=18, opts=None, residual=False, use_coeff=False, resnet_layer=None, video_input=False,
                  f_maps=512, stride=(1, 1)):
@@ -295,15 +322,7 @@ class fs_encoder_v2(nn.Module):
         self.block_3 = _iresnet_layer(128, 256, 14)
         self.block_4 = _iresnet_layer(256, 512, 3)
         if opts is not None and getattr(opts, "arcface_model_path", None):
-            sd = torch.load(opts.arcface_model_path, map_location="cpu")
-            remap = {"conv1": "conv.0", "bn1": "conv.1", "prelu": "conv.2", "layer1": "block_1", "layer2": "block_2",
-                     "layer3": "block_3", "layer4": "block_4"}
-            mine = {}
-            for k, v in sd.items():
-                head = k.split(".")[0]
-                if head in remap:
-                    mine[remap[head] + k[len(head):]] = v
-            self.load_state_dict(mine, strict=False)
+            _load_arcface_trunk(self, opts.arcface_model_path)
         s = stride[0] if isinstance(stride, (tuple, list)) else stride
         self.content_layer = nn.Sequential(
             nn.BatchNorm2d(256, eps=1e-05), nn.Conv2d(256, 512, kernel_size=3, stride=1, padding=1, bias=False),

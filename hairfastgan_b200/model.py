@@ -131,6 +131,15 @@ class ScaledLeakyReLU(nn.Module):
         return F.leaky_relu(input, negative_slope=self.negative_slope) * math.sqrt(2)
 
 
+def _expect_shape(t: torch.Tensor, shape, what: str) -> None:
+    """The C ABI receives raw pointers: every tensor's full shape is checked here, where the reference would raise
+    a shape error from torch (None in `shape` = any size)."""
+    ok = t.dim() == len(shape) and all(e is None or int(a) == int(e) for a, e in zip(t.shape, shape))
+    if not ok:
+        want = "[" + ", ".join("*" if e is None else str(e) for e in shape) + "]"
+        raise RuntimeError(f"{what}: expected shape {want}, got {list(t.shape)}")
+
+
 class _PackedConv:
     """Lazily (re)packed tensor-core operand of one ModulatedConv2d, keyed on the parameter version."""
 
@@ -196,6 +205,13 @@ class ModulatedConv2d(nn.Module):
         batch, cin, height, width = input.shape
         if cin != self.in_channel:
             raise RuntimeError(f"ModulatedConv2d: expected {self.in_channel} input channels, got {cin}")
+        _expect_shape(style, (batch, self.modulation.weight.shape[1]), "ModulatedConv2d style")
+        if noise is not None:
+            f = 2 if self.upsample else 1
+            if noise.dim() != 4 or noise.shape[0] not in (1, batch):
+                raise RuntimeError(f"StyledConv noise: expected [1|{batch}, 1, {height * f}, {width * f}], "
+                                   f"got {list(noise.shape)}")
+            _expect_shape(noise, (None, 1, height * f, width * f), "StyledConv noise")
         desc, blob = self._packed.get(self, dtype)
         x = _f32c(input)
         st = _f32c(style)
@@ -284,6 +300,12 @@ class ToRGB(nn.Module):
         lib = _lib.lib()
         _lib.use_device(input.device.index)
         batch, cin, height, width = input.shape
+        _expect_shape(input, (batch, self.conv.in_channel, height, width), "ToRGB input")
+        _expect_shape(style, (batch, self.conv.modulation.weight.shape[1]), "ToRGB style")
+        if skip is not None:
+            _expect_shape(skip, (batch, 3, height // 2, width // 2), "ToRGB skip")
+            if height % 2 or width % 2:
+                raise RuntimeError("ToRGB: a skip needs an even-sized input")
         x, st = _f32c(input), _f32c(style)
         w, mw, mb = _f32c(self.conv.weight), _f32c(self.conv.modulation.weight), _f32c(self.conv.modulation.bias)
         bias = _f32c(self.bias)
@@ -470,6 +492,7 @@ class Generator(nn.Module):
         lib = _lib.lib()
         batch = latent.shape[0]
         n_layers = self.log_size - 2
+        _expect_shape(latent, (batch, self.n_latent, self.style_dim), "Generator latent")
 
         # which layers execute -- mirror of the reference loop (model.py:534-557)
         run = [start_layer == 0] + [False] * n_layers
@@ -504,21 +527,24 @@ class Generator(nn.Module):
                 if nz is None:
                     r = 4 if i == 0 else 2 ** ((i + 1) // 2 + 2)
                     nz = lat.new_empty(batch, 1, r, r).normal_()
+                r = 4 if i == 0 else 2 ** ((i + 1) // 2 + 2)
+                if nz.dim() != 4 or nz.shape[0] not in (1, batch):
+                    raise RuntimeError(f"noise[{i}]: expected [1|{batch}, 1, {r}, {r}], got {list(nz.shape)}")
+                _expect_shape(nz, (None, 1, r, r), f"Generator noise[{i}]")
                 nz = _f32c(nz)
-                if nz.shape[0] not in (1, batch):
-                    raise RuntimeError(f"noise[{i}] has batch {nz.shape[0]}, expected 1 or {batch}")
                 keep.append(nz)
                 io.noise[i], io.noise_batch[i] = nz.data_ptr(), nz.shape[0]
         io.start_layer, io.end_layer = start_layer, end_layer
         if start_layer > 0:
             if layer_in is None:
                 raise RuntimeError("Generator: start_layer > 0 needs layer_in (reference model.py:546)")
+            r_in = 4 * 2 ** (start_layer - 1)           # the input of layer k is the output of layer k-1
+            _expect_shape(layer_in, (batch, self.channels[r_in], r_in, r_in), "Generator layer_in")
             li = _f32c(layer_in)
-            if li.shape[0] != batch:
-                raise RuntimeError("Generator: layer_in batch does not match the latent batch")
             keep.append(li)
             io.layer_in = li.data_ptr()
             if skip is not None:
+                _expect_shape(skip, (batch, 3, r_in, r_in), "Generator skip")
                 sk = _f32c(skip)
                 keep.append(sk)
                 io.skip_in = sk.data_ptr()
@@ -539,6 +565,10 @@ class Generator(nn.Module):
                 if float(feature_scale) != 1.0:
                     raise RuntimeError("Generator: insert_feature is implemented for feature_scale == 1.0 only "
                                        "(HairFast always runs min(1, 1e-4 * 1e5) = 1.0)")
+                # features_in[i] replaces the INPUT of the conv at latent index i (FSE model.py:527-560): the output
+                # of styled conv i-1, resolution 4 * 2^(i // 2)
+                r_f = 4 * 2 ** (i // 2)
+                _expect_shape(f, (batch, self.channels[r_f], r_f, r_f), f"Generator features_in[{i}]")
                 ff = _f32c(f)
                 keep.append(ff)
                 io.feature_in[i] = ff.data_ptr()

@@ -55,4 +55,11 @@ class FusedLeakyReLU(nn.Module):
 
 
 def fused_leaky_relu(input, bias, negative_slope=0.2, scale=2 ** 0.5):
+    if input.device.type == "cpu" and input.dim() == 2:
+        # The one CPU use the reference makes of this op at inference: Net.build_PCA_model (models/Net.py:50-55) moves
+        # the mapping MLP to the CPU and pushes 1e6 z vectors through EqualLinear(activation='fused_lrelu')
+        # (models/stylegan2/model.py:153-157) when <ckpt>_PCA.npz is missing -- an init-time one-off on [N, 512]
+        # vectors, restated from the reference's own CPU branch (op/fused_act.py:86-93).  Feature maps (the hot path)
+        # stay CUDA-only: a CPU image tensor still raises below.
+        return torch.nn.functional.leaky_relu(input + bias.view(1, -1), negative_slope=negative_slope) * scale
     return fused_bias_act(input, bias, None, 3, 0, negative_slope, scale)
