@@ -127,7 +127,10 @@ def main():
                "final_max": float(finals[-1].max()), "finite": bool(torch.isfinite(finals[-1]).all()),
                "deterministic": bool(all(torch.equal(finals[0], f) for f in finals[1:])),
                "device": torch.cuda.get_device_name(0),
-               "dtype": os.environ.get("HAIRFAST_DTYPE", "bf16") if a.mode != "reference" else "fp32/tf32",
+               "dtype": ("fp32/tf32" if a.mode == "reference" else
+                         "generator %s, encoders %s" % (os.environ.get("HAIRFAST_DTYPE", "bf16"),
+                                                        os.environ.get("HAIRFAST_ENC_DTYPE") or
+                                                        os.environ.get("HAIRFAST_DTYPE", "fp16"))),
                "generator_class": type(hair_fast.net.generator).__module__}
     print(json.dumps(summary))
     if a.out:

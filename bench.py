@@ -44,7 +44,6 @@ GFLOP_PP_PER_TRIPLE = 2 * GFLOP_PP_ENC_IMG + GFLOP_PP_RES
 GFLOP_SEG_512 = 27.5                                      # BiSeNet (ResNet-18 context path + heads) on one 512^2 image
 GFLOP_SEG_PER_TRIPLE = 3 * GFLOP_SEG_512 + 2 * 4 * GFLOP_SEG_512      # 3 calls at 512^2, 2 at 1024^2
 GFLOP_PER_TRIPLE = GFLOP_GEN_PER_TRIPLE + GFLOP_ENC_PER_TRIPLE + GFLOP_PP_PER_TRIPLE + GFLOP_SEG_PER_TRIPLE   # = 3063.8
-GFLOP_CPU_SAMPLE = GFLOP_FULL + GFLOP_E4E_IMG + GFLOP_FSE_IMG + GFLOP_PP_ENC_IMG + GFLOP_PP_RES + GFLOP_SEG_512  # 1074.1
 ROOFLINE_US_PER_IMG = 142.5                               # SURVEY Appendix A, sum of per-layer maxima
 
 
@@ -104,6 +103,35 @@ def census(T: int):
             (0, 8, T, None), (4, 8, T, 32), (5, 8, T, 64)]
 
 
+def make_host_inputs(T: int, seed: int):
+    """Pinned host inputs of one step of T triples (seeded: rank r of an N-GPU run uses seed 100 + r, so any rank's
+    batch can be rebuilt anywhere for the output-equality check)."""
+    import torch
+    calls = census(T)
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    lat = [torch.randn(b, 18, 512, generator=g).pin_memory() for (_, _, b, _) in calls]
+    lin = [None if r is None else torch.randn(b, 512, r, r, generator=g).pin_memory() for (_, _, b, r) in calls]
+    # 256^2 network inputs: e4e (3T), e4e (2T), FSE (3T), PostProcess source (T) and target (T)
+    img = [(torch.rand(n * T, 3, 256, 256, generator=g) * 2 - 1).pin_memory() for n in (3, 2, 3, 1, 1)]
+    # BiSeNet inputs: the three 512^2 images of a triple (Embedding.py:81) and two 1024^2 ones (Alignment / Blending)
+    img += [(torch.rand(3 * T, 3, 512, 512, generator=g) * 2 - 1).pin_memory(),
+            (torch.rand(T, 3, 1024, 1024, generator=g) * 2 - 1).pin_memory()]
+    return {"T": T, "calls": calls, "lat": lat, "lin": lin, "img": img}
+
+
+def to_device(inp, dev):
+    return {"T": inp["T"], "calls": inp["calls"], "lat": [t.to(dev) for t in inp["lat"]],
+            "lin": [None if t is None else t.to(dev) for t in inp["lin"]], "img": [t.to(dev) for t in inp["img"]]}
+
+
+def image_checksums(final):
+    """Two 64-bit integer checksums per image over the raw fp32 bit patterns (bit-exact comparison across ranks)."""
+    import torch
+    v = final.contiguous().view(torch.int32).view(final.shape[0], -1).to(torch.int64)
+    w = (torch.arange(v.shape[1], device=v.device, dtype=torch.int64) % 65521) + 1
+    return torch.stack([v.sum(1), (v * w).sum(1)], 1)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -147,26 +175,17 @@ def run_ours(args, rank, world, local_rank):
                 m.running_var.uniform_(0.5, 1.5)
                 m.running_mean.normal_(0, 0.1)
     bcast_bytes = 0
-    if world > 1:                                     # weights replicated: one NCCL broadcast at init
+    if world > 1:                                     # weights replicated: one coalesced NCCL broadcast per net at init
         for net in (gen, e4e, fse, pp_enc, pp_res, seg):
             bcast_bytes += sharding.broadcast_module_(net, src=0)
-    calls = census(T)
-    g = torch.Generator(device="cpu").manual_seed(100 + rank)
-    host_lat = [torch.randn(b, 18, 512, generator=g).pin_memory() for (_, _, b, _) in calls]
-    host_lin = [None if r is None else torch.randn(b, 512, r, r, generator=g).pin_memory() for (_, _, b, r) in calls]
-    # 256^2 network inputs: e4e (3T), e4e (2T), FSE (3T), PostProcess source (T) and target (T)
-    host_img = [(torch.rand(n * T, 3, 256, 256, generator=g) * 2 - 1).pin_memory() for n in (3, 2, 3, 1, 1)]
-    # BiSeNet inputs: the three 512^2 images of a triple (Embedding.py:81) and two 1024^2 ones (Alignment / Blending)
-    host_img += [(torch.rand(3 * T, 3, 512, 512, generator=g) * 2 - 1).pin_memory(),
-                 (torch.rand(T, 3, 1024, 1024, generator=g) * 2 - 1).pin_memory()]
-    dev_lat = [t.to(dev) for t in host_lat]
-    dev_lin = [None if t is None else t.to(dev) for t in host_lin]
-    dev_img = [t.to(dev) for t in host_img]
+    host = make_host_inputs(T, 100 + rank)
+    devin = to_device(host, dev)
     host_out = torch.empty(T, 3, 1024, 1024).pin_memory()
     launches = [0]
 
-    def compute(img, lats, lins, skip_fse_recon=False):
+    def compute(inp, skip_fse_recon=False):
         """The hot path of T triples through the public module API (what swap()'s stages call)."""
+        img, lats, lins, calls = inp["img"], inp["lat"], inp["lin"], inp["calls"]
         n0 = lib.hf_total_launch_count()
         for net, x in ((e4e, img[0]), (e4e, img[1]), (fse, img[2])):   # Embedding.py:71,74 / :51
             net(x)
@@ -186,12 +205,12 @@ def run_ours(args, rank, world, local_rank):
         launches[0] += lib.hf_total_launch_count() - n0
         return final
 
-    def step(_e2e: bool = False):
-        return compute(dev_img, dev_lat, dev_lin)
+    def step():
+        return compute(devin)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
-    def timed(_e2e: bool, steps: int, warmup: int):
+    def timed(steps: int, warmup: int):
         for _ in range(warmup):
             step()
         torch.cuda.synchronize()
@@ -219,12 +238,12 @@ def run_ours(args, rank, world, local_rank):
     # ends only after the last download has finished.
     h2d_stream, d2h_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
-    host_all = host_img + host_lat + [t for t in host_lin if t is not None]
+    host_all = host["img"] + host["lat"] + [t for t in host["lin"] if t is not None]
     dbuf = [[torch.empty(t.shape, device=dev) for t in host_all] for _ in range(2)]
     hout = [host_out, torch.empty(T, 3, 1024, 1024).pin_memory()]
     ev_ready = [torch.cuda.Event() for _ in range(2)]
     ev_done = [torch.cuda.Event() for _ in range(2)]
-    n_img, n_lat = len(host_img), len(host_lat)
+    n_img, n_lat = len(host["img"]), len(host["lat"])
 
     def e2e_step(k: int):
         s = k & 1
@@ -235,8 +254,9 @@ def run_ours(args, rank, world, local_rank):
             ev_ready[s].record(h2d_stream)
         main_stream.wait_event(ev_ready[s])
         it = iter(dbuf[s][n_img + n_lat:])
-        lins = [None if t is None else next(it) for t in host_lin]
-        final = compute(dbuf[s][:n_img], dbuf[s][n_img:n_img + n_lat], lins)
+        lins = [None if t is None else next(it) for t in host["lin"]]
+        final = compute({"T": T, "calls": host["calls"], "img": dbuf[s][:n_img], "lat": dbuf[s][n_img:n_img + n_lat],
+                         "lin": lins})
         ev_done[s].record(main_stream)
         final.record_stream(d2h_stream)
         with torch.cuda.stream(d2h_stream):
@@ -265,10 +285,10 @@ def run_ours(args, rank, world, local_rank):
         return sharding.max_over_ranks(e0.elapsed_time(e1), dev)
 
     if args.profile_step:                             # for `ncu --profile-from-start off`: exactly one step
-        step(False)
+        step()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
-        step(False)
+        step()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
         return None
@@ -277,32 +297,64 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     for _ in range(2):
-        step(False)                                   # also gives nvidia-smi time to start sampling
+        step()                                        # also gives nvidia-smi time to start sampling
     torch.cuda.synchronize()
     first = sampler.mark()
-    ms, n_launch = timed(False, args.steps, args.warmup)
+    ms, n_launch = timed(args.steps, args.warmup)
     ms_e2e = timed_e2e(args.steps, max(3, args.warmup // 2))
     clocks = sampler.stop(first) if rank == 0 else None
 
     extra = {"nccl_broadcast_bytes_at_init": bcast_bytes}
+
+    # ---- per-triple outputs of the N-GPU run must equal the 1-GPU run bit for bit.  After the
+    # timed region every rank recomputes its step under swap()'s seed (utils/seed.py:22-28, 3407) and checksums each
+    # triple's final image; rank 0 rebuilds every other rank's batch from its seed, computes it on ITS GPU under the same
+    # seed, and compares the checksums gathered over NCCL.
+    if world > 1:
+        torch.manual_seed(3407)
+        mine = image_checksums(compute(devin))
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        ok = True
+        if rank == 0:
+            for r in range(1, world):
+                other = to_device(make_host_inputs(T, 100 + r), dev)
+                torch.manual_seed(3407)
+                ok = ok and bool(torch.equal(image_checksums(compute(other)), gathered[r]))
+                del other
+        flag = torch.tensor([int(ok)], device=dev)
+        dist.broadcast(flag, src=0)
+        extra["shard_output_equality"] = {"checked_ranks": world - 1, "triples_per_rank": T,
+                                          "bit_identical_to_single_gpu": bool(flag.item())}
+        if not bool(flag.item()):
+            raise RuntimeError("N-GPU per-triple outputs differ from the single-GPU computation")
+
+    def avg_ms(fn, n=5):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(n):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / n
+
+    if rank == 0 and world == 1:
+        # single-triple latency: the census exactly as ONE swap() issues it (B = 3 / 2 / 1 per call, Appendix B)
+        one = to_device(make_host_inputs(1, 7), dev)
+        ms_t1 = avg_ms(lambda: compute(one), n=10)
+        extra["latency_T1"] = {"latency_ms_per_triple": round(ms_t1, 3), "triples_per_s": round(1e3 / ms_t1, 2),
+                               "note": "hot path of ONE triple, calls at B=3/2/1 as swap() issues them, HBM-resident"}
+        del one
     if rank == 0 and world == 1 and args.no_extras:
         extra["roofline"] = roofline
         extra["roofline_b4"] = roofline_b4
     elif rank == 0 and world == 1:
-        def avg_ms(fn, n=5):
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            tot = 0.0
-            for _ in range(n):
-                flush.fill_(1)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); fn(); e1.record(); e1.synchronize()
-                tot += e0.elapsed_time(e1)
-            return tot / n
         # opt-in SURVEY 8f-2 fast path (install(skip_fse_reconstruction=True)): the step without the FSE reconstruction
         # forward that swap() discards (445.6 GFLOP/triple), the noise still drawn
-        ms_skip = avg_ms(lambda: compute(dev_img, dev_lat, dev_lin, skip_fse_recon=True))
+        ms_skip = avg_ms(lambda: compute(devin, skip_fse_recon=True))
         extra["fse_recon_skipped"] = {"value": round(T / (ms_skip * 1e-3), 3), "unit": "triples/s",
                                       "ms_per_step": round(ms_skip, 3),
                                       "note": "same outputs for swap(); not the default, see INTEGRATION.md"}
@@ -342,19 +394,101 @@ def run_ours(args, rank, world, local_rank):
         ms_u1 = avg_ms(lambda: OP.upfirdn2d(xu, k2 * 4, pad=(1, 1)))
         xs3 = torch.randn(48, 3, 512, 512, device=dev)
         ms_u2 = avg_ms(lambda: OP.upfirdn2d(xs3, k2 * 4, up=2, pad=(2, 1)))
+        xd = torch.randn(64, 3, 1024, 1024, device=dev)
+        ms_d2 = avg_ms(lambda: OP.upfirdn2d(xd, k2, down=2, pad=(1, 1)))
         gbs = {"fused_leaky_relu_4x64x1024x1024": 2 * xa.numel() * 4 / ms_a / 1e6,
                "upfirdn2d_up1_k4_pad11_256x1025x1025": (xu.numel() + 256 * 1024 * 1024) * 4 / ms_u1 / 1e6,
-               "upfirdn2d_up2_k4_pad21_144x512x512": (xs3.numel() * 5) * 4 / ms_u2 / 1e6}
+               "upfirdn2d_up2_k4_pad21_144x512x512": (xs3.numel() * 5) * 4 / ms_u2 / 1e6,
+               "upfirdn2d_down2_k4_pad11_192x1024x1024": (xd.numel() * 1.25) * 4 / ms_d2 / 1e6}
         extra["ops_hbm"] = {k: {"GB/s": round(v, 1), "frac_of_measured_copy_peak": round(v / hbm, 3)}
                             for k, v in gbs.items()}
-        del xa, xu, xs3
+        del xa, xu, xs3, xd
         extra["roofline"] = roofline
         extra["roofline_b4"] = roofline_b4
     if world > 1:
         dist.destroy_process_group()
-    h2d = sum(t.numel() * 4 for t in host_lat) + sum(t.numel() * 4 for t in host_lin if t is not None) \
-        + sum(t.numel() * 4 for t in host_img)
+    h2d = sum(t.numel() * 4 for t in host["lat"]) + sum(t.numel() * 4 for t in host["lin"] if t is not None) \
+        + sum(t.numel() * 4 for t in host["img"])
     return ms, ms_e2e, n_launch, clocks, extra, h2d
+
+
+def _json_tail(stdout: str):
+    for line in reversed(stdout.splitlines()):
+        line = line.strip()
+        if line.startswith("{"):
+            return json.loads(line)
+    raise RuntimeError("no JSON line in: " + stdout[-500:])
+
+
+def comparator_legs(args):
+    """Side measurements that need OTHER processes (the GPU is free: our own run has finished): the stock reference on
+    the same B200 (`reference_gpu`), the full HairFast.swap() under the overlay vs the stock one (`full_swap`), and our
+    own step with every network in bf16 / fp16 (`value_by_dtype`).  Each is a bounded child run; a failure is reported
+    in the line, never hidden."""
+    from baseline import refenv
+    out = {}
+    env = dict(os.environ)
+    env.pop("OMP_NUM_THREADS", None)
+
+    def child(cmd, timeout, extra_env=None):
+        e = dict(env)
+        e.update(extra_env or {})
+        p = subprocess.run(cmd, capture_output=True, text=True, env=e, timeout=timeout, cwd=ROOT)
+        if p.returncode != 0:
+            raise RuntimeError(p.stderr[-600:])
+        return _json_tail(p.stdout)
+
+    by_dtype = {}
+    for dt in ("bf16", "fp16"):
+        try:
+            d = child([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3", "--triples",
+                       str(args.triples), "--no-extras", "--no-cpu-baseline", "--no-comparators"], 900,
+                      {"HAIRFAST_DTYPE": dt, "HAIRFAST_ENC_DTYPE": dt})
+            by_dtype[dt] = {"value": d["value"], "e2e": d["e2e"]["value"], "latency_T1_ms": d["latency_T1"]["latency_ms_per_triple"]}
+        except Exception as ex:   # noqa: BLE001
+            by_dtype[dt] = {"error": str(ex)[-300:]}
+    out["value_by_dtype"] = {"unit": "triples/s", "note": "every network in that operand type (HAIRFAST_DTYPE=...)",
+                             **by_dtype}
+    if not refenv.available():
+        out["reference_gpu"] = {"unavailable": "reference checkout not staged (tools/stage_reference.sh)"}
+        out["full_swap"] = {"unavailable": "reference checkout not staged (tools/stage_reference.sh)"}
+        return out
+    census_py = os.path.join(ROOT, "baseline", "ref_census.py")
+    ref = {}
+    for T in sorted({1, args.triples}):
+        try:
+            d = child([sys.executable, census_py, "--device", "cuda", "--triples", str(T), "--steps", "3", "--warmup",
+                       "2"], 1500)
+            ref[f"T{T}"] = {"triples_per_s": round(d["triples_per_s"], 3), "ms_per_step": round(d["ms_per_step"], 2),
+                            "peak_mem_gb": d["peak_mem_gb"]}
+            ref["arith"] = d["arith"]
+        except Exception as ex:   # noqa: BLE001
+            ref[f"T{T}"] = {"error": str(ex)[-300:]}
+    ref["what"] = ("the SAME census on the stock reference modules on this B200: F.conv2d(groups=B)/conv_transpose2d "
+                   "through cuDNN + its two JIT kernels (models/stylegan2/model.py:238-279), baseline/ref_census.py")
+    out["reference_gpu"] = ref
+    swap = {}
+    work = os.environ.get("HAIRFAST_WORK", "/tmp/hairfast_work")
+    for mode in ("reference", "overlay", "overlay_fast"):
+        try:
+            d = child([sys.executable, os.path.join(ROOT, "baseline", "run_swap.py"), "--mode", mode, "--work", work,
+                       "--reps", "5", "--warmup", "2"], 1500)
+            ts = d["timings"]
+            n = len(ts)
+            swap[mode] = {"full_swap_ms": round(sum(t["gpu_ms"] for t in ts) / n, 2),
+                          "hot_path_ms": round(sum(t["hot_path_ms"] for t in ts) / n, 2),
+                          "out_of_scope_ms": round(sum(t["out_of_scope_ms"] for t in ts) / n, 2),
+                          "per_module_ms": {k: round(sum(t["per_module_ms"].get(k, 0.0) for t in ts) / n, 2)
+                                            for k in ts[-1]["per_module_ms"]},
+                          "dtype": d["dtype"], "deterministic": d["deterministic"]}
+        except Exception as ex:   # noqa: BLE001
+            swap[mode] = {"error": str(ex)[-300:]}
+    swap["what"] = ("BASELINE configs[2]: the unmodified HairFast(get_parser().parse_args([])).swap() on one synthetic "
+                    "1024^2 triple, synthetic checkpoints (baseline/run_swap.py): stock reference vs the same checkout "
+                    "under hairfastgan_b200.install(); hot path = generator + e4e + FS encoder + PostProcess conv "
+                    "stack + BiSeNet (forward hooks, CUDA events); out of scope = SEAN, CLIP stand-in, mask nets, glue")
+    out["full_swap"] = swap
+    return out
 
 
 def time_dominant_kernel(gen, dev, B=4):
@@ -396,41 +530,100 @@ def time_dominant_kernel(gen, dev, B=4):
             "launch_ms": round(ms.value, 4), "traffic": traffic}
 
 
-def cpu_oracle_sample(threads=None):
-    """The reference algorithm on host cores (oracle port; the Python reference cannot travel to the GPU box): one
-    full 1024^2 generator forward + one e4e + one FSE + one PostProcess FeatureEncoderMult forward, the PostProcess
-    FeatureiResnet and one BiSeNet forward at 512^2, B=1 (1074.1 of the 3063.8 GFLOP of a triple), scaled to
-    triples/s."""
+CENSUS_COUNTS = {"gen_full": 5, "gen_0_3": 5, "gen_3_3": 3, "gen_4_8": 1, "gen_5_8": 1, "e4e": 5, "fse": 3,
+                 "pp_enc": 2, "pp_res": 1, "seg_512": 3, "seg_1024": 2}          # SURVEY Appendix B, per triple
+CPU_SAMPLE = ("every distinct call of the SURVEY App. B census once at B=1 (generator full / 0->3 / 3->3 / 4->8 / 5->8, "
+              "e4e, FSE, FeatureEncoderMult, FeatureiResnet, BiSeNet 512^2 and 1024^2); per-triple time = "
+              "sum(count x time) = the whole census, nothing FLOP-scaled")
+
+
+def cpu_threads():
+    """All host cores, stated.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must not inherit that
+    silently (round 1: 64 threads at N=1, 1 thread under torchrun -> a 4.5x swing of the denominator)."""
+    return os.cpu_count() or 1
+
+
+def cpu_census_reference(steps: int, warmup: int):
+    """The STOCK reference modules (staged checkout, baseline/_ref) on the host cores: baseline/ref_census.py."""
+    env = dict(os.environ)
+    env.pop("OMP_NUM_THREADS", None)
+    cmd = [sys.executable, os.path.join(ROOT, "baseline", "ref_census.py"), "--device", "cpu", "--steps", str(steps),
+           "--warmup", str(warmup), "--threads", str(cpu_threads())]
+    p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=3000)
+    if p.returncode != 0:
+        raise RuntimeError("ref_census.py failed: " + p.stderr[-2000:])
+    d = json.loads([l for l in p.stdout.splitlines() if l.strip()][-1])
+    return d["s_per_triple"], d["cores"], "reference", d["per_call_s"]
+
+
+def cpu_census_port(steps: int, warmup: int):
+    """Same census on the oracle port (used only when the reference checkout is not staged)."""
     import torch
     from oracle import stylegan2_oracle as O
     from oracle import encoders_oracle as EO
+    from oracle import bisenet_oracle as BO
     import hairfastgan_b200.encoders as E          # parameter containers only (CPU); the math below is the oracle's
     import hairfastgan_b200.postprocess as PP
+    import hairfastgan_b200.bisenet as SEG
     torch.set_grad_enabled(False)
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(cpu_threads())
+    g = torch.Generator().manual_seed(0)
     p = O.synth_generator_params(size=1024, seed=0)
-    lat = torch.randn(1, 18, 512, generator=torch.Generator().manual_seed(0))
+    lat = torch.randn(1, 18, 512, generator=g)
     noise = O.synth_noise(1024, batch=1, seed=1)
+    li = {r: torch.randn(1, 512, r, r, generator=g) for r in (16, 32, 64)}
     pe = EO.synth_params_like(E.Encoder4Editing(50, "ir_se", types.SimpleNamespace(stylegan_size=1024)), 11)
     pf = EO.synth_params_like(E.fs_encoder_v2(n_styles=18, opts=None, stride=(2, 2)), 21)
     pm = EO.synth_params_like(PP.FeatureEncoderMult(fs_layers=[9], opts=None), 31)
     pr = EO.synth_params_like(PP.FeatureiResnet([[1024, 2], [768, 2], [512, 2]]), 41)
-    x = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(12)) * 2 - 1
-    xr = torch.randn(1, 1024, 64, 64, generator=torch.Generator().manual_seed(13))
-    from oracle import bisenet_oracle as BO
-    import hairfastgan_b200.bisenet as SEG
     ps = EO.synth_params_like(SEG.BiSeNet(n_classes=19), 51)
-    xs = torch.rand(1, 3, 512, 512, generator=torch.Generator().manual_seed(14)) * 2 - 1
-    t0 = time.perf_counter()
-    BO.bisenet_ref(ps, xs)
-    O.generator_ref(p, lat, noise)
-    EO.e4e_ref(pe, x)
-    EO.fse_ref(pf, x)
-    EO.feature_encoder_mult_ref(pm, x)
-    EO.feature_iresnet_ref(pr, xr)
-    dt = time.perf_counter() - t0
-    return dt, (GFLOP_CPU_SAMPLE / GFLOP_PER_TRIPLE) / dt, torch.get_num_threads()
+    x = torch.rand(1, 3, 256, 256, generator=g) * 2 - 1
+    xr = torch.randn(1, 1024, 64, 64, generator=g)
+    x512, x1024 = torch.rand(1, 3, 512, 512, generator=g) * 2 - 1, torch.rand(1, 3, 1024, 1024, generator=g) * 2 - 1
+    calls = {"gen_full": lambda: O.generator_ref(p, lat, noise), "gen_0_3": lambda: O.generator_ref(p, lat, noise, 0, 3),
+             "gen_3_3": lambda: O.generator_ref(p, lat, noise, 3, 3, li[16]),
+             "gen_4_8": lambda: O.generator_ref(p, lat, noise, 4, 8, li[32]),
+             "gen_5_8": lambda: O.generator_ref(p, lat, noise, 5, 8, li[64]),
+             "e4e": lambda: EO.e4e_ref(pe, x), "fse": lambda: EO.fse_ref(pf, x),
+             "pp_enc": lambda: EO.feature_encoder_mult_ref(pm, x), "pp_res": lambda: EO.feature_iresnet_ref(pr, xr),
+             "seg_512": lambda: BO.bisenet_ref(ps, x512), "seg_1024": lambda: BO.bisenet_ref(ps, x1024)}
+    tot, last = [], {}
+    for it in range(warmup + steps):
+        t = 0.0
+        for name, fn in calls.items():
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            last[name] = round(dt, 4)
+            t += CENSUS_COUNTS[name] * dt
+        if it >= warmup:
+            tot.append(t)
+    return sum(tot) / len(tot), torch.get_num_threads(), "port", last
+
+
+def cpu_census(steps: int = 1, warmup: int = 0):
+    """(seconds per triple, threads, kind, per-call seconds) of the hot-path census on the host cores."""
+    from baseline import refenv
+    if refenv.available() and os.environ.get("HAIRFAST_CPU_ARM", "reference") != "port":
+        return cpu_census_reference(steps, warmup)
+    return cpu_census_port(steps, warmup)
+
+
+WORKLOAD = ""
+
+
+def dtype_string():
+    gen = os.environ.get("HAIRFAST_DTYPE", "bf16")
+    enc = os.environ.get("HAIRFAST_ENC_DTYPE") or os.environ.get("HAIRFAST_DTYPE", "fp16")
+    return f"generator {gen} / encoders {enc} operands, f32 accumulate"
+
+
+def config_of(T: int, world: int):
+    """`config` of the JSON line -- identical for our arm and the reference arm (the driver compares them)."""
+    return {"workload": WORKLOAD, "triples_per_step_per_gpu": T, "size": 1024,
+            "parallelism": f"dp{world} (independent triples per rank, no step collective)",
+            "l2": "256 MiB flush write between timed steps; value: per-step CUDA events summed; e2e: one event "
+                  "pair around all steps, uploads/downloads double-buffered on side streams"}
 
 
 _REAL_STDOUT = None
@@ -462,6 +655,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-network / per-operator side measurements")
     ap.add_argument("--profile-step", action="store_true", help="run one step between cudaProfilerStart/Stop, no JSON")
+    ap.add_argument("--no-comparators", action="store_true",
+                    help="skip the child-process legs (reference_gpu, full_swap, value_by_dtype)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -471,25 +666,21 @@ def main():
                 "@64^2) + BiSeNet on 3 images at 512^2 and 2 at 1024^2 per triple = 3063.8 GFLOP/triple (SURVEY "
                 "App. B / 8d config 3 / 8f-3), synthetic weights; out-of-scope nets (SEAN/CLIP/mask) and stage glue "
                 "excluded")
-    sample = ("one full 1024^2 generator forward + one e4e + one FSE + one FeatureEncoderMult forward + the "
-              "FeatureiResnet + one BiSeNet forward at 512^2, B=1 = 1074.1 of 3063.8 GFLOP per triple, scaled")
+    global WORKLOAD
+    WORKLOAD = workload
 
     if args.impl == "reference":
         if rank != 0:
             return
-        times = []
-        for i in range(args.warmup + args.steps):
-            dt, tps, thr = cpu_oracle_sample()
-            if i >= args.warmup:
-                times.append(dt)
-        dt = sum(times) / len(times)
-        val = (GFLOP_CPU_SAMPLE / GFLOP_PER_TRIPLE) / dt
+        s_per_triple, thr, kind, per_call = cpu_census(args.steps, args.warmup)
+        val = 1.0 / s_per_triple
         emit(({
             "impl": "reference", "metric": "hair_swap_triples_per_sec", "value": val, "unit": "triples/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_triple * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "sample": sample},
-            "cpu_baseline": {"value": val, "unit": "triples/s", "cores": thr, "kind": "port", "sample": sample},
+            "config": config_of(args.triples, world),
+            "cpu_baseline": {"value": val, "unit": "triples/s", "cores": thr, "kind": kind, "sample": CPU_SAMPLE,
+                             "per_call_s": per_call},
             "e2e": {"value": val, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return
@@ -508,11 +699,8 @@ def main():
         "metric": "hair_swap_triples_per_sec", "value": round(value, 3), "unit": "triples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": os.environ.get("HAIRFAST_DTYPE", "bf16") + " operands, f32 accumulate", "data": "synthetic",
-        "config": {"workload": workload, "triples_per_step_per_gpu": T, "size": 1024,
-                   "parallelism": f"dp{world} (independent triples per rank, no step collective)",
-                   "l2": "256 MiB flush write between timed steps; value: per-step CUDA events summed; e2e: one event "
-                         "pair around all steps, uploads/downloads double-buffered on side streams"},
+        "dtype": dtype_string(), "data": "synthetic",
+        "config": config_of(T, world),
         "tflops_algorithmic": round(GFLOP_PER_TRIPLE * value / 1e3, 1),
         # whole-step fraction of the conv roofline: algorithmic FLOP/s over all GPUs / (N x measured bf16 peak)
         "frac_of_tensor_peak": round(GFLOP_PER_TRIPLE * value / 1e3 / (world * peaks()["tf_burst"]), 4),
@@ -521,10 +709,12 @@ def main():
         "gpu_launches": n_launch, "clocks": clocks,
     }
     out.update(extra)
+    if world == 1 and not args.no_extras and not args.no_comparators:
+        out.update(comparator_legs(args))
     if world == 1 and not args.no_cpu_baseline:
-        dt, tps, thr = cpu_oracle_sample()
-        out["cpu_baseline"] = {"value": round(tps, 5), "unit": "triples/s", "cores": thr, "kind": "port",
-                               "sample": f"oracle port, B=1 ({dt:.1f} s): " + sample}
+        s_per_triple, thr, kind, per_call = cpu_census(1, 0)
+        out["cpu_baseline"] = {"value": round(1.0 / s_per_triple, 5), "unit": "triples/s", "cores": thr, "kind": kind,
+                               "sample": f"{s_per_triple:.1f} s per triple: " + CPU_SAMPLE}
     emit(out)
 
 

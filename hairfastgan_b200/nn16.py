@@ -8,8 +8,20 @@ from typing import Optional
 
 import torch
 
+import os
+
 from . import _lib
-from .model import default_dtype
+
+
+def default_dtype() -> int:
+    """16-bit operand / activation type of the ENCODER family (e4e, FS encoder, PostProcess stack, BiSeNet): fp16 unless
+    HAIRFAST_ENC_DTYPE or HAIRFAST_DTYPE says bf16.  These are BatchNorm-normalised backbones (eval-mode BN folded into
+    the weights, inputs in [-1, 1]; the ArcFace trunk even ships an fp16 autocast switch, arcface/iresnet.py:146) whose
+    activations stay far inside fp16's range, and fp16's 11-bit significand matches the TF32 arithmetic of the
+    reference's own GPU path -- ~8x closer than bf16 over the ~50 chained convolutions.  The generator
+    keeps bf16 by default (`model.default_dtype`): StyleGAN2 activations times style scales are not bounded."""
+    v = os.environ.get("HAIRFAST_ENC_DTYPE") or os.environ.get("HAIRFAST_DTYPE") or "fp16"
+    return _lib.HF_BF16 if v.lower() in ("bf16", "bfloat16") else _lib.HF_F16
 
 
 def torch_dtype(dt: Optional[int] = None):

@@ -17,6 +17,12 @@ def dtype_name():
     return "fp16" if os.environ.get("HAIRFAST_DTYPE", "bf16").lower() in ("fp16", "f16", "half") else "bf16"
 
 
+def enc_dtype_name():
+    """dtype of the encoder family (hairfastgan_b200/nn16.default_dtype): fp16 unless an env var says bf16."""
+    v = os.environ.get("HAIRFAST_ENC_DTYPE") or os.environ.get("HAIRFAST_DTYPE") or "fp16"
+    return "bf16" if v.lower() in ("bf16", "bfloat16") else "fp16"
+
+
 def rel_err(y: torch.Tensor, ref: torch.Tensor):
     y = y.detach().float().cpu()
     ref = ref.detach().float().cpu()

@@ -10,13 +10,16 @@ import torch
 import torch.nn.functional as F
 
 from oracle import encoders_oracle as EO
-from tests.gpu_util import dtype_name, record, rel_err
+from tests.gpu_util import enc_dtype_name as dtype_name, record, rel_err
 
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
 
 # stated tolerance: max-abs error / RMS of the reference output after ~50 chained 16-bit convolutions
 TOL_ENC = {"bf16": 8e-2, "fp16": 1.5e-2}
+# the B=32 FSE content map [2,512,16,16] is a max over 2.6e5 elements of a deeper tap; stated separately for the
+# opt-in bf16 mode (measured 8.6e-2), same as TOL_ENC in the default fp16 mode
+TOL_ENC_MAP_B32 = {"bf16": 1e-1, "fp16": 1.5e-2}
 TOL_CONV = {"bf16": 4e-2, "fp16": 6e-3}     # one conv incl. 16-bit rounding of its input and output
 
 
@@ -245,5 +248,4 @@ def test_config4_inversion_batch32(N):
     lo, co = EO.fse_ref(pf, xc[30:32], content_stride=2)
     e1, e2 = rel_err(lat32[30:32], lo)[0], rel_err(c32[30:32], co)[0]
     record("fse_b32_tail_vs_oracle", latent_rel_max_err=e1, content_rel_max_err=e2)
-    # the content map is a max over 262k elements: measured 8.6e-2 (bf16) on these samples vs 4.8e-2 on the golden pair
-    assert e1 < TOL_ENC[dtype_name()] and e2 < 1.5 * TOL_ENC[dtype_name()], (e1, e2)
+    assert e1 < TOL_ENC[dtype_name()] and e2 < TOL_ENC_MAP_B32[dtype_name()], (e1, e2)

@@ -134,6 +134,36 @@ def test_generator1024_golden_and_batch_properties(M, golden_dir):
     assert float((img4[3] - one[0]).abs().max()) < 1e-4
 
 
+# north_star: "max-abs on generator RGB".  Stated ABSOLUTE tolerance on a unit-range image (RGB in [-1, 1], what a
+# trained generator emits): bf16 operands 2e-2, fp16 operands 3e-3.
+TOL_RGB_ABS_UNIT = {"bf16": 2e-2, "fp16": 3e-3}
+
+
+def test_generator1024_unit_range_rgb_max_abs(M, golden_dir):
+    """The reference golden of the synthetic 1024^2 generator spans +-8.9; the image is LINEAR in the ToRGB weights
+    and biases (rgb = sum over layers of Up(W_rgb (s' x) + b), model.py:356-365), so scaling all of them by
+    alpha = 1 / max|golden| gives exactly alpha * golden from the reference -- a unit-range image with a known
+    answer, on which the max-abs error is asserted in absolute terms."""
+    g = np.load(os.path.join(golden_dir, "generator1024.npz"))
+    alpha = 1.0 / float(g["image_absmax"])
+    params = O.synth_generator_params(size=1024, seed=0)
+    for k in params:
+        if k.startswith("to_rgb") and (k.endswith("conv.weight") or k.endswith(".bias") and params[k].ndim == 4):
+            params[k] = params[k] * alpha
+    gen = M.Generator(1024, 512, 8)
+    gen.load_state_dict(params, strict=True)
+    gen = gen.cuda().eval()
+    lat = torch.randn(1, 18, 512, generator=torch.Generator().manual_seed(0)).cuda()
+    noise = _cuda_list(O.synth_noise(1024, batch=1, seed=1))
+    img, _ = gen([lat], input_is_latent=True, noise=noise)
+    ref_sub, ref_rows = torch.from_numpy(g["image_sub"]) * alpha, torch.from_numpy(g["image_rows"]) * alpha
+    assert float(ref_sub.abs().max()) <= 1.0 + 1e-6
+    err = max(float((img[:, :, ::16, ::16].cpu() - ref_sub).abs().max()),
+              float((img[:, :, 511:513].cpu() - ref_rows).abs().max()))
+    record("gen1024_unit_range_abs", abs_max_err=err, range="[-1,1]")
+    assert err < TOL_RGB_ABS_UNIT[dtype_name()], err
+
+
 def test_fse_generator_variant_golden(M, golden_dir):
     """the FeatureStyleEncoder generator copy (features_in at idx 5, feature_scale=1,
     return_features=True) -- the call Trainer.get_image makes (trainer.py:295)."""

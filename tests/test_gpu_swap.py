@@ -17,19 +17,24 @@ import pytest
 import torch
 
 from baseline import refenv
-from tests.gpu_util import ROOT, dtype_name, record
+from tests.gpu_util import ROOT, record
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not refenv.available(), reason="reference not staged (tools/stage_reference.sh)")]
 
 WORK = os.environ.get("HAIRFAST_WORK", "/tmp/hairfast_work")
+# "default" = nothing set in the environment: generator bf16, encoder family fp16 (what a user of install() gets)
+HF_DTYPES = ["default", "fp16"]
 
 # Stated tolerance of the FINAL 1024^2 image (values in [0,1]) against the stock reference run on the same GPU, same
 # seeds.  The pipeline has discrete decisions (BiSeNet arg-max labels -> 256^2 masks -> F-space blends), so a small set
 # of pixels near label boundaries can move by more than the arithmetic error; the bound is therefore on the mean and on
 # a high quantile, with the max reported.
-TOL_FINAL_MEAN = {"bf16": 1.5e-2, "fp16": 4e-3}
-TOL_FINAL_Q99 = {"bf16": 6e-2, "fp16": 2e-2}
+# Measured on B200 (round 2): all-bf16 mean 1.7e-4 / q99 5.8e-4 / max 1.6e-3.
+TOL_FINAL_MEAN = {"default": 1e-3, "bf16": 1e-3, "fp16": 3e-4}
+TOL_FINAL_Q99 = {"default": 4e-3, "bf16": 4e-3, "fp16": 1.2e-3}
+TOL_FINAL_MAX = {"default": 2e-2, "bf16": 2e-2, "fp16": 1e-2}
+_reference_arm = {}
 
 
 def _run(mode, out, extra=()):
@@ -41,12 +46,15 @@ def _run(mode, out, extra=()):
 
 
 @pytest.fixture(scope="module")
-def arms(tmp_path_factory):
+def arms(tmp_path_factory, hf_dtype):
     d = tmp_path_factory.mktemp("swap")
-    res = {m: _run(m, str(d / f"{m}.pt")) for m in ("reference", "overlay", "overlay_fast")}
+    if "reference" not in _reference_arm:                             # the stock arm does not depend on our dtype
+        _reference_arm["reference"] = _run("reference", str(d / "reference.pt"))
+    res = {"reference": _reference_arm["reference"], "dtype": hf_dtype or "default"}
+    res.update({m: _run(m, str(d / f"{m}.pt")) for m in ("overlay", "overlay_fast")})
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", f"swap_arms_{dtype_name()}.json"), "w") as f:
-        json.dump({m: r["summary"] for m, r in res.items()}, f, indent=1)
+    with open(os.path.join(ROOT, "gpurun_out", f"swap_arms_{res['dtype']}.json"), "w") as f:
+        json.dump({m: r["summary"] for m, r in res.items() if isinstance(r, dict)}, f, indent=1)
     return res
 
 
@@ -72,10 +80,10 @@ def test_swap_matches_stock_reference(arms):
             emb[k] = float((w - v).abs().max()) / (float(v.pow(2).mean().sqrt()) + 1e-12)
         else:
             emb[k] = float((w != v).float().mean())                   # label disagreement rate of the 256^2 masks
-    record("swap_final_vs_stock_reference", mean_abs=mean, q99_abs=q99, max_abs=mx,
+    dt = arms["dtype"]
+    record("swap_final_vs_stock_reference", mode=dt, mean_abs=mean, q99_abs=q99, max_abs=mx,
            embed={k: round(x, 5) for k, x in emb.items()})
-    dt = dtype_name()
-    assert mean <= TOL_FINAL_MEAN[dt] and q99 <= TOL_FINAL_Q99[dt], (mean, q99, mx, emb)
+    assert mean <= TOL_FINAL_MEAN[dt] and q99 <= TOL_FINAL_Q99[dt] and mx <= TOL_FINAL_MAX[dt], (mean, q99, mx, emb)
 
 
 def test_skip_fse_reconstruction_gives_the_same_image(arms):
