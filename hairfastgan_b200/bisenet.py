@@ -15,8 +15,8 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import nn16
-from .encoders import _params_key
+from . import graphs, nn16
+from .encoders import _PackCacheMixin, _params_key
 
 __all__ = ["BiSeNet", "ConvBNReLU", "BiSeNetOutput", "AttentionRefinementModule", "ContextPath", "FeatureFusionModule",
            "Resnet18", "BasicBlock"]
@@ -163,13 +163,17 @@ class _PackedOutput:
         wp[:self.n_classes] = w
         self.conv_out = nn16.PackedConv2d(wp)
 
-    def __call__(self, x16, height, width):
+    def lowres(self, x16):
         h, _, _ = self.conv(x16, shift=self.shift, act=3)
         _, _, low = self.conv_out(h, want_y16=False, want_y32=True)         # [B,32,h,w] fp32, classes first
+        return low
+
+    def __call__(self, x16, height, width):
+        low = self.lowres(x16)
         return nn16.bilinear_upsample_nchw(low, self.n_classes, height, width), low
 
 
-class BiSeNet(nn.Module):
+class BiSeNet(_PackCacheMixin, nn.Module):
     """model.py:217-244."""
 
     def __init__(self, n_classes, *args, **kwargs):
@@ -204,12 +208,14 @@ class BiSeNet(nn.Module):
         self._pk = pk
         return pk
 
-    @torch.no_grad()
-    def forward(self, x, return_lowres: bool = False):
+    def _trunk(self, x):
+        """Everything up to the three head inputs (fuse, feat16_up, feat32_up) -- model.py:226-234."""
         if self.training:
             raise RuntimeError("BiSeNet: only eval-mode (running BatchNorm statistics) forward is implemented")
         if not x.is_cuda:
             raise RuntimeError("BiSeNet: input must be a CUDA tensor (no CPU fallback)")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise RuntimeError(f"BiSeNet: expected [B,3,H,W], got {list(x.shape)}")
         H, W = x.shape[2:]
         if H % 32 or W % 32:
             raise NotImplementedError(f"BiSeNet: input size {H}x{W} must be a multiple of 32")
@@ -241,6 +247,23 @@ class BiSeNet(nn.Module):
         feat, _, _ = pk["ffm"][0](fcat, shift=pk["ffm"][1], act=3)
         atten = nn16.se_gate(feat, self.ffm.conv1.weight, self.ffm.conv2.weight)
         fuse, _ = nn16.scale_add(feat, atten, feat)                                                 # feat*atten + feat
+        return pk, fuse, feat16_up, feat32_up, H, W
+
+    def _check(self, x):
+        if self.training:
+            raise RuntimeError("BiSeNet: only eval-mode (running BatchNorm statistics) forward is implemented")
+        if not torch.is_tensor(x) or not x.is_cuda:
+            raise RuntimeError("BiSeNet: input must be a CUDA tensor (no CPU fallback)")
+
+    @torch.no_grad()
+    def forward(self, x, return_lowres: bool = False):
+        self._check(x)
+        if return_lowres:
+            return self._forward_impl(x, True)
+        return graphs.run(self, "fwd", _params_key(self), self._forward_impl, x)
+
+    def _forward_impl(self, x, return_lowres: bool = False):
+        pk, fuse, feat16_up, feat32_up, H, W = self._trunk(x)
         # ---- heads + bilinear upsampling (model.py:235-241)
         o, lo = pk["out"](fuse, H, W)
         o16, lo16 = pk["out16"](feat16_up, H, W)
@@ -248,3 +271,17 @@ class BiSeNet(nn.Module):
         if return_lowres:
             return [t[:, :pk["out"].n_classes] for t in (lo, lo16, lo32)]
         return o, o16, o32
+
+    @torch.no_grad()
+    def parse_labels(self, x):
+        """``self(x)[0].argmax(1)`` -- what face parsing keeps of the network (my_parsing_util.py:87-88,
+        models/Net.py:108-115) -- as int64 labels [B,H,W], bit-identical to the arg-max of ``forward``'s first output:
+        the two auxiliary heads (training-time supervision, model.py:236-237) are not evaluated and the upsampling is
+        fused with the arg-max (``hf_bilinear_argmax_nchw_f32``), so the 19 x H x W fp32 logits are never written."""
+        self._check(x)
+        return graphs.run(self, "labels", _params_key(self), self._parse_impl, x)
+
+    def _parse_impl(self, x):
+        pk, fuse, _, _, H, W = self._trunk(x)
+        low = pk["out"].lowres(fuse)
+        return nn16.bilinear_argmax_nchw(low, pk["out"].n_classes, H, W)

@@ -170,6 +170,29 @@ int hf_dilate_erode_f32(const float* mask, float* dilate, float* erode, void* wo
                              (cudaStream_t)stream);
 }
 
+int hf_bilinear_argmax_nchw_f32(const float* x, long long* labels, int batch, int channels, int in_channels, int h,
+                                int w, int height, int width, void* stream) {
+  int rc = ensure_device_current();
+  if (rc) return rc;
+  return launch_bilinear_argmax(x, labels, batch, channels, in_channels, h, w, height, width, (cudaStream_t)stream);
+}
+
+int hf_align_masks_f32(const float* hair_mask1, const float* hair_mask2, const float* hair_mask_target, float* masks,
+                       int n, void* stream) {
+  int rc = ensure_device_current();
+  if (rc) return rc;
+  return launch_align_masks(hair_mask1, hair_mask2, hair_mask_target, masks, n, (cudaStream_t)stream);
+}
+
+int hf_fspace_blend_f32(const float* first, const float* const* src, const float* const* mask, const float* scale_a,
+                        const float* scale_b, float* out, int n_stage, int channels, int height, int width,
+                        int mask_height, int mask_width, void* stream) {
+  int rc = ensure_device_current();
+  if (rc) return rc;
+  return launch_fspace_blend(first, src, mask, scale_a, scale_b, out, n_stage, channels, height, width, mask_height,
+                             mask_width, (cudaStream_t)stream);
+}
+
 int hf_bilinear_upsample_nchw_f32(const float* x, float* y, int batch, int channels, int in_channels, int h, int w,
                                   int height, int width, void* stream) {
   int rc = ensure_device_current();

@@ -71,6 +71,12 @@ int launch_bicubic_down(const float* x, const float* k, float* y, int planes, in
                         cudaStream_t st);
 int launch_dilate_erode(const float* mask, float* dilate, float* erode, float* ws, int planes, int H, int W,
                         int iterations, cudaStream_t st);
+int launch_bilinear_argmax(const float* x, long long* labels, int B, int C, int Cin, int h, int w, int H, int W,
+                           cudaStream_t st);
+int launch_align_masks(const float* hm1, const float* hm2, const float* hmx, float* out, int n, cudaStream_t st);
+int launch_fspace_blend(const float* first, const float* const* src, const float* const* mask, const float* scale_a,
+                        const float* scale_b, float* out, int n_stage, int C, int Ho, int Wo, int Hm, int Wm,
+                        cudaStream_t st);
 int launch_bilinear_up_nchw(const float* x, float* y, int B, int C, int Cin, int h, int w, int H, int W,
                             cudaStream_t st);
 int launch_se_gate(const void* x16, const float* fc1, const float* fc2, float* out, float* ws, int B, int HW, int C,

@@ -138,6 +138,148 @@ __global__ void __launch_bounds__(256) upfirdn2d_up2_k4_kernel(const float* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Round-2 fast paths: register sliding windows, no shared memory, no block-level synchronisation.
+// A warp owns a strip of RS rows x 128 columns and walks down it; every lane keeps its 4 (or 2x8) outputs' partial
+// sums in registers and each input row is fetched ONCE per strip (plus the 3 / 2 halo rows, which the neighbouring
+// strip of the same CTA has just pulled into L1/L2).  All global accesses of a warp are row-contiguous (512 B per
+// row); the 4x4 FIR costs 64 FMAs per float4 of output, well under the issue budget of an HBM-bound kernel.
+// ---------------------------------------------------------------------------------------------
+// up = 1, down = 1, 4x4 taps, any pad >= 0 (the Blur after the transposed convolution, model.py:77-93).
+template <int RS>
+__global__ void __launch_bounds__(256) upfirdn2d_up1_k4_strip_kernel(const float* __restrict__ x,
+                                                                     float* __restrict__ y,
+                                                                     const float* __restrict__ k, int in_h, int in_w,
+                                                                     int out_h, int out_w, int px0, int py0) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ox = blockIdx.x * 128 + lane * 4;
+  const int oy0 = (blockIdx.y * 8 + warp) * RS;
+  if (oy0 >= out_h) return;
+  float kr[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kr[i] = __ldg(k + 15 - i);           // flipped taps: kr[a*4+b] = k[3-a][3-b]
+  const float* xp = x + (size_t)blockIdx.z * in_h * in_w;
+  float* yp = y + (size_t)blockIdx.z * out_h * out_w;
+  const int ix0 = ox - px0;
+  const bool interior = ix0 >= 0 && ix0 + 6 < in_w;
+  const bool vec_store = ((out_w & 3) == 0) && ox + 3 < out_w;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
+  for (int r0 = 0; r0 < RS + 3; r0 += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u;
+      const int iy = oy0 - py0 + r;
+      float v[7];
+      const bool row_ok = (r < RS + 3) && iy >= 0 && iy < in_h;
+      const float* rp = xp + (size_t)(row_ok ? iy : 0) * in_w + ix0;
+      if (row_ok && interior) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) v[c] = __ldg(rp + c);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) v[c] = (row_ok && ix0 + c >= 0 && ix0 + c < in_w) ? __ldg(rp + c) : 0.f;
+      }
+      // input row r feeds output rows r - a (a = tap row); (r - a) & 3 == (u - a) & 3 because r0 % 4 == 0
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[(u - a) & 3][j] = fmaf(v[j + b], kr[a * 4 + b], acc[(u - a) & 3][j]);
+      const int orow = r - 3;                                        // complete once its a = 3 row has arrived
+      const int slot = (u + 1) & 3;
+      if (orow >= 0 && orow < RS && oy0 + orow < out_h) {
+        float* dst = yp + (size_t)(oy0 + orow) * out_w + ox;
+        if (vec_store) {
+          __stcs(reinterpret_cast<float4*>(dst), make_float4(acc[slot][0], acc[slot][1], acc[slot][2], acc[slot][3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (ox + j < out_w) dst[j] = acc[slot][j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[slot][j] = 0.f;
+    }
+  }
+}
+
+// up = 2, down = 1, 4x4 taps, pad (2,1): the RGB-skip Upsample (model.py:35-53), out = 2 x in.  Output parity (py,px)
+// has 2x2 live taps: out[2y+py][2x+px] = sum_{a,b in {0,1}} in[y-1+py+a][x-1+px+b] * kf[py+2a][px+2b].
+// A lane owns 4 input columns (8 output columns, two float4 stores per output row) and slides a 3-row window.
+template <int RS>
+__global__ void __launch_bounds__(256) upfirdn2d_up2_k4_strip_kernel(const float* __restrict__ x,
+                                                                     float* __restrict__ y,
+                                                                     const float* __restrict__ k, int in_h, int in_w) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * 128 + lane * 4;
+  const int y0 = (blockIdx.y * 8 + warp) * RS;
+  if (y0 >= in_h || x0 >= in_w) return;
+  float kr[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kr[i] = __ldg(k + 15 - i);
+  const float* xp = x + (size_t)blockIdx.z * in_h * in_w;
+  const int out_w = 2 * in_w;
+  float* yp = y + (size_t)blockIdx.z * (2 * in_h) * out_w;
+  const bool interior = x0 >= 1 && x0 + 4 < in_w;
+  const bool full = x0 + 3 < in_w && (in_w & 1) == 0;               // 2*in_w % 4 == 0 and all 8 outputs exist
+  float win[3][6];
+  auto load_row = [&](int iy, float* v) {
+    const bool row_ok = iy >= 0 && iy < in_h;
+    const float* rp = xp + (size_t)(row_ok ? iy : 0) * in_w + x0 - 1;
+    if (row_ok && interior) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) v[c] = __ldg(rp + c);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) v[c] = (row_ok && x0 - 1 + c >= 0 && x0 - 1 + c < in_w) ? __ldg(rp + c) : 0.f;
+    }
+  };
+  load_row(y0 - 1, win[0]);
+  load_row(y0, win[1]);
+#pragma unroll 1
+  for (int r0 = 0; r0 < RS; r0 += 3) {
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int yy = y0 + r0 + u;
+      // rows yy-1, yy, yy+1 live in slots u % 3, (u+1) % 3, (u+2) % 3
+      load_row((r0 + u < RS && yy < in_h) ? yy + 1 : -1, win[(u + 2) % 3]);
+      if (r0 + u < RS && yy < in_h) {
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+              float s = 0.f;
+#pragma unroll
+              for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+                  s = fmaf(win[(u + py + a) % 3][i + px + b], kr[(py + 2 * a) * 4 + px + 2 * b], s);
+              o[2 * i + px] = s;
+            }
+          float* dst = yp + (size_t)(2 * yy + py) * out_w + 2 * x0;
+          if (full) {
+            __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+            __stcs(reinterpret_cast<float4*>(dst) + 1, make_float4(o[4], o[5], o[6], o[7]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (2 * x0 + j < out_w) dst[j] = o[j];
+          }
+        }
+      }
+    }
+  }
+}
+
 // General path: any up/down/pad (incl. negative pads = crop) and any kernel size.
 __global__ void __launch_bounds__(256) upfirdn2d_general_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                 const float* __restrict__ k, int in_h, int in_w,
@@ -183,7 +325,16 @@ int launch_upfirdn2d(const float* x, float* y, const float* k, int planes, int i
   if (planes == 0) return HF_OK;
   const bool k4 = (kh == 4 && kw == 4);
   const bool sym = (up_x == up_y && down_x == down_y);
-  if (k4 && sym && up_x == 1 && (down_x == 1 || down_x == 2) && planes <= 65535) {
+  if (k4 && sym && up_x == 1 && down_x == 1 && planes <= 65535 && px0 >= 0 && py0 >= 0 && px1 >= 0 && py1 >= 0) {
+    constexpr int RS = 16;                                   // 8 warps x 16 rows x 128 columns per CTA
+    dim3 grid(cdiv(out_w, 128), cdiv(out_h, 8 * RS), planes);
+    upfirdn2d_up1_k4_strip_kernel<RS><<<grid, 256, 0, st>>>(x, y, k, in_h, in_w, out_h, out_w, px0, py0);
+  } else if (k4 && sym && up_x == 2 && down_x == 1 && planes <= 65535 && px0 == 2 && py0 == 2 && px1 == 1 &&
+             py1 == 1) {
+    constexpr int RS = 12;                                   // 8 warps x 12 input rows x 128 input columns per CTA
+    dim3 grid(cdiv(in_w, 128), cdiv(in_h, 8 * RS), planes);
+    upfirdn2d_up2_k4_strip_kernel<RS><<<grid, 256, 0, st>>>(x, y, k, in_h, in_w);
+  } else if (k4 && sym && up_x == 1 && (down_x == 1 || down_x == 2) && planes <= 65535) {
     if (down_x == 1) {
       dim3 grid(cdiv(out_w, 64), cdiv(out_h, 32), planes);
       upfirdn2d_up1_k4_kernel<1, 32><<<grid, 256, 0, st>>>(x, y, k, in_h, in_w, out_h, out_w, px0, py0);

@@ -259,6 +259,12 @@ int launch_gate_add_up(const void* x16, const float* gate, const float* addvec, 
 // F.interpolate(x, (H, W), mode='bilinear', align_corners=True) on fp32 NCHW (model.py:239-241): the first C of
 // Cin channel planes of x (the logit convolution pads its 19 classes to 32 output channels).
 // ------------------------------------------------------------------------------------------------
+// the one interpolation expression of all three kernels below (explicit roundings: the fused arg-max kernel must
+// reproduce the logits of the plain upsampling kernel bit for bit)
+__device__ __forceinline__ float lerp_rn(float t, float a, float b) {
+  return __fmaf_rn(t, b, __fmul_rn(__fsub_rn(1.f, t), a));
+}
+
 __global__ void __launch_bounds__(256) bilinear_up_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int C,
                                                                int Cin, int h, int w, int H, int W4, int64_t rows) {
   // One CTA per output row (b, c, Y), grid-stride.  The two source rows are blended once into shared memory
@@ -277,7 +283,7 @@ __global__ void __launch_bounds__(256) bilinear_up_nchw_kernel(const float* __re
     const float* p0 = x + (((size_t)b * Cin + c) * h + y0) * w;
     const float* p1 = x + (((size_t)b * Cin + c) * h + y1) * w;
     __syncthreads();
-    for (int xs = threadIdx.x; xs < w; xs += blockDim.x) srow[xs] = (1.f - ly) * __ldg(p0 + xs) + ly * __ldg(p1 + xs);
+    for (int xs = threadIdx.x; xs < w; xs += blockDim.x) srow[xs] = lerp_rn(ly, __ldg(p0 + xs), __ldg(p1 + xs));
     __syncthreads();
     float* yrow = y + (size_t)row * W;
     for (int X4 = threadIdx.x; X4 < W4; X4 += blockDim.x) {
@@ -288,7 +294,7 @@ __global__ void __launch_bounds__(256) bilinear_up_nchw_kernel(const float* __re
         const int x0 = (int)fx;
         const int x1 = x0 + 1 < w ? x0 + 1 : x0;
         const float lx = fx - x0;
-        o[j] = (1.f - lx) * srow[x0] + lx * srow[x1];
+        o[j] = lerp_rn(lx, srow[x0], srow[x1]);
       }
       *reinterpret_cast<float4*>(yrow + X4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
     }
@@ -312,8 +318,64 @@ __global__ void __launch_bounds__(256) bilinear_up_nchw_scalar_kernel(const floa
     const float* p = x + ((size_t)b * Cin + c) * h * w;
     const float a00 = __ldg(p + (size_t)y0 * w + x0), a01 = __ldg(p + (size_t)y0 * w + x1);
     const float a10 = __ldg(p + (size_t)y1 * w + x0), a11 = __ldg(p + (size_t)y1 * w + x1);
-    y[i] = (1.f - ly) * ((1.f - lx) * a00 + lx * a01) + ly * ((1.f - lx) * a10 + lx * a11);
+    y[i] = lerp_rn(lx, lerp_rn(ly, a00, a10), lerp_rn(ly, a01, a11));       // rows first, like the row kernel
   }
+}
+
+// Fused `F.interpolate(logits, (H, W), 'bilinear', align_corners=True)` + `argmax(dim=1)` (BiSeNet.forward
+// model.py:239 followed by FaceParsing_tensor.parsing_img, my_parsing_util.py:87-88): the [B,C,H,W] fp32 logits
+// (76 B per pixel for 19 classes) never exist; 8 B of label per pixel are written.  One CTA per output row (b, Y): the
+// C vertically blended source rows go to shared memory, then every thread scans the C classes of its pixels with the
+// same arithmetic as bilinear_up_nchw_kernel, keeping the FIRST maximum (torch.argmax's tie rule).
+__global__ void __launch_bounds__(256) bilinear_argmax_kernel(const float* __restrict__ x, long long* __restrict__ labels,
+                                                              int C, int Cin, int h, int w, int H, int W, int rows) {
+  extern __shared__ float srow[];                       // [C][w]
+  const float ry = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, rx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = row / H, Y = row - b * H;
+    const float fy = Y * ry;
+    const int y0 = (int)fy;
+    const int y1 = y0 + 1 < h ? y0 + 1 : y0;
+    const float ly = fy - y0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * w; i += blockDim.x) {
+      const int c = i / w, xs = i - c * w;
+      const float* p = x + ((size_t)b * Cin + c) * h * w;
+      srow[i] = lerp_rn(ly, __ldg(p + (size_t)y0 * w + xs), __ldg(p + (size_t)y1 * w + xs));
+    }
+    __syncthreads();
+    long long* out = labels + (size_t)row * W;
+    for (int X = threadIdx.x; X < W; X += blockDim.x) {
+      const float fx = X * rx;
+      const int x0 = (int)fx;
+      const int x1 = x0 + 1 < w ? x0 + 1 : x0;
+      const float lx = fx - x0;
+      float best = lerp_rn(lx, srow[x0], srow[x1]);
+      int arg = 0;
+      for (int c = 1; c < C; ++c) {
+        const float v = lerp_rn(lx, srow[c * w + x0], srow[c * w + x1]);
+        if (v > best) { best = v; arg = c; }
+      }
+      out[X] = arg;
+    }
+  }
+}
+
+int launch_bilinear_argmax(const float* x, long long* labels, int B, int C, int Cin, int h, int w, int H, int W,
+                           cudaStream_t st) {
+  HF_REQUIRE(x && labels && B > 0 && C > 0 && Cin >= C && h > 0 && w > 0 && H > 0 && W > 0,
+             "bilinear_argmax: bad arguments");
+  const size_t smem = (size_t)C * w * sizeof(float);
+  HF_REQUIRE(smem <= 200 * 1024, "bilinear_argmax: %d classes x %d source columns do not fit in shared memory", C, w);
+  const int64_t rows = (int64_t)B * H;
+  HF_REQUIRE(rows < (int64_t)2000000000, "bilinear_argmax: too many rows");
+  if (smem > 48 * 1024)
+    HF_CUDA_OK(cudaFuncSetAttribute(bilinear_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::min<int64_t>(rows, (int64_t)num_sms() * 8);
+  bilinear_argmax_kernel<<<grid, 256, smem, st>>>(x, labels, C, Cin, h, w, H, W, (int)rows);
+  HF_LAUNCH_OK("bilinear_argmax");
+  count_launch();
+  return HF_OK;
 }
 
 int launch_bilinear_up_nchw(const float* x, float* y, int B, int C, int Cin, int h, int w, int H, int W,

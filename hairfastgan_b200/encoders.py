@@ -23,12 +23,29 @@ from collections import namedtuple
 import torch
 from torch import nn
 
-from . import nn16
+from . import graphs, nn16
 from .model import EqualLinear
 
 
 def _params_key(module: nn.Module):
-    return tuple((p.data_ptr(), p._version) for p in list(module.parameters()) + list(module.buffers()))
+    """Version key of every parameter / buffer (repack when a weight changes).  Walking the module tree costs
+    milliseconds for a 600-tensor encoder -- as much as its kernels at swap()'s batch sizes -- so the tensor LIST is
+    cached on the module; `nn.Module._apply` (.to / .cuda / .float: the calls that replace buffer objects) drops it
+    (`_PackCacheMixin`), `load_state_dict` copies in place and shows up in `_version`."""
+    ts = module.__dict__.get("_hf_tensors")
+    if ts is None:
+        ts = list(module.parameters()) + list(module.buffers())
+        module.__dict__["_hf_tensors"] = ts
+    return tuple([(t.data_ptr(), t._version) for t in ts])
+
+
+class _PackCacheMixin:
+    """Invalidate the cached tensor list (and with it the packed operands / captured graphs) on device / dtype moves."""
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop("_hf_tensors", None)
+        self.__dict__.pop("_hf_graphs", None)
+        return super()._apply(fn, *args, **kwargs)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -156,19 +173,23 @@ class _PackedHeads:
         for d in range(1, depth):
             self.rest.append(nn16.PackedConv2d(torch.cat([c[d].weight for c in convs], 0), stride=2, groups=self.n))
             self.rest_bias.append(torch.cat([c[d].bias for c in convs], 0).detach().float())
-        self.lin_w = torch.stack([h.linear.weight.detach().float() * h.linear.scale for h in heads], 0)   # [n,512,512]
-        self.lin_b = torch.stack([h.linear.bias.detach().float() * h.linear.lr_mul for h in heads], 0)    # [n,512]
+        # EqualLinear of every head (psp_encoders.py:47,52-53) = one grouped 1x1 convolution on the [B,1,1,n*512] map
+        lin_w = torch.cat([h.linear.weight.detach().float() * h.linear.scale for h in heads], 0)          # [n*512,512]
+        self.lin = nn16.PackedConv2d(lin_w.reshape(lin_w.shape[0], lin_w.shape[1], 1, 1), groups=self.n)
+        self.lin_b = torch.cat([h.linear.bias.detach().float() * h.linear.lr_mul for h in heads], 0).contiguous()
 
     def __call__(self, feat16):
         x, _, _ = self.first(feat16, shift=self.first_bias, act=2, slope0=0.01)
         for conv, bias in zip(self.rest, self.rest_bias):
             x, _, _ = conv(x, shift=bias, act=2, slope0=0.01)
         b = x.shape[0]
-        v = x.reshape(b, self.n, -1).float()                                   # [B, heads, 512]  (spatial is 1x1)
-        return torch.einsum("bhi,hoi->bho", v, self.lin_w) + self.lin_b        # EqualLinear per head
+        if x.shape[1] != 1 or x.shape[2] != 1:
+            raise RuntimeError(f"GradualStyleBlock: expected a 1x1 map before the linear layer, got {list(x.shape)}")
+        _, _, y = self.lin(x, shift=self.lin_b, want_y16=False, want_y32=True)  # [B, heads*512, 1, 1] fp32
+        return y.reshape(b, self.n, -1)                                         # EqualLinear per head
 
 
-class Encoder4Editing(nn.Module):
+class Encoder4Editing(_PackCacheMixin, nn.Module):
     def __init__(self, num_layers, mode="ir", opts=None):
         super().__init__()
         assert num_layers in [50, 100, 152], "num_layers should be 50,100, or 152"
@@ -215,6 +236,9 @@ class Encoder4Editing(nn.Module):
             raise RuntimeError("Encoder4Editing: only eval-mode (running BatchNorm statistics) forward is implemented")
         if not x.is_cuda:
             raise RuntimeError("Encoder4Editing: input must be a CUDA tensor (no CPU fallback)")
+        return graphs.run(self, "e4e", _params_key(self), self._forward_impl, x)
+
+    def _forward_impl(self, x):
         pk = self._pack()
         blocks = pk["blocks"]
         x16 = nn16.to_nhwc16(x, c_pad=32)
@@ -308,7 +332,7 @@ def _load_arcface_trunk(module, path):
     module.load_state_dict(mine, strict=False)
 
 
-class fs_encoder_v2(nn.Module):
+class fs_encoder_v2(_PackCacheMixin, nn.Module):
     def __init__(self, n_styles=18, opts=None, residual=False, use_coeff=False, resnet_layer=None, video_input=False,
                  f_maps=512, stride=(1, 1)):
         super().__init__()
@@ -356,8 +380,11 @@ class fs_encoder_v2(nn.Module):
               "stem_slope": self.conv[2].weight.detach().float().contiguous(),
               "stages": [[b.packed() for b in blk] for blk in (self.block_1, self.block_2, self.block_3, self.block_4)],
               "content": branches,
-              "style_w": torch.stack([s.weight.detach().float() for s in self.styles], 0),     # [18,512,8640]
-              "style_b": torch.stack([s.bias.detach().float() for s in self.styles], 0)}
+              # the n_styles nn.Linear(960*9, 512) heads (feature_style_encoder.py:44-45,62-64) stacked: ONE 1x1
+              # convolution [B,1,1,8640] -> [B, n_styles*512]
+              "style": nn16.PackedConv2d(torch.cat([s.weight.detach().float() for s in self.styles], 0)[:, :, None, None]),
+              "style_b": torch.cat([s.bias.detach().float() for s in self.styles], 0).contiguous(),
+              "n_styles": len(self.styles)}
         self._pk = pk
         return pk
 
@@ -388,11 +415,22 @@ class fs_encoder_v2(nn.Module):
                         h, _, _ = br["conv1"](cb, shift=br["shift1"], act=1, slope=br["slope"])
                         _, _, c = br["conv2"](h, shift=br["shift2"], want_y16=False, want_y32=True)
                         content.append(c)
-        f = torch.cat(feats, dim=1).reshape(x.shape[0], -1)                               # [B, 960*9]
-        out = torch.einsum("bi,hoi->bho", f, pk["style_w"]) + pk["style_b"]                # 18 x nn.Linear(8640,512)
+        b = x.shape[0]
+        f = torch.cat(feats, dim=1).reshape(b, 1, 1, -1).to(nn16.torch_dtype())           # [B,1,1,960*9], x.view(B,-1) order
+        _, _, out = pk["style"](f, shift=pk["style_b"], want_y16=False, want_y32=True)     # 18 x nn.Linear(8640,512)
+        out = out.reshape(b, pk["n_styles"], -1)
         return out, content
 
     @torch.no_grad()
     def forward(self, x):
-        out, content = self._trunk(x)
+        out, content = self._graphed_trunk(x)
         return out, content[0]
+
+    def _graphed_trunk(self, x):
+        """`_trunk` through the CUDA-graph cache (graphs.py); the eval / device checks run before any capture."""
+        name = type(self).__name__
+        if self.training:
+            raise RuntimeError(f"{name}: only eval-mode (running BatchNorm statistics) forward is implemented")
+        if not x.is_cuda:
+            raise RuntimeError(f"{name}: input must be a CUDA tensor (no CPU fallback)")
+        return graphs.run(self, "trunk", _params_key(self), self._trunk, x)

@@ -1,0 +1,113 @@
+"""CUDA-graph replay of the encoder-family forwards at swap()'s batch sizes.
+
+One `swap()` calls e4e at B = 3 and 2, the FS encoder at B = 3, FeatureEncoderMult at B = 1 twice, FeatureiResnet once
+and BiSeNet five times at B = 1: 100-350 kernel launches each, every one a ctypes call from Python.
+At these sizes the kernels finish faster than the host can enqueue them, so the hot path of a single triple was
+launch-bound (round-2 measurement: 26 ms of hot path in a swap whose kernels need well under half of that).  Each
+network forward is a fixed launch sequence for a given input shape, so after the second call with the same signature it
+is captured once (`torch.cuda.CUDAGraph`, the library only enqueues on the current stream and allocates nothing) and
+replayed: input copied into the graph's static buffer, one `cudaGraphLaunch`, outputs cloned out.
+
+* keyed on (network, input shape / dtype / device, parameter version key): a weight change recaptures
+* batch <= HAIRFAST_GRAPH_MAX_BATCH (default 8): the graph's private pool holds one set of activations per signature,
+  which is only wanted at latency-bound sizes (the throughput path at B = 48 stays eager)
+* no RNG inside these networks; the generator (17 `normal_()` draws per forward, GPU-bound even at B = 1) stays eager
+* HAIRFAST_CUDA_GRAPHS=0 disables it; a failed capture disables it for that signature (eager CUDA path, never a CPU one)
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+__all__ = ["run", "enabled", "stats"]
+
+_STATS = {"captures": 0, "replays": 0, "eager": 0, "failed": 0}
+
+
+def enabled() -> bool:
+    return os.environ.get("HAIRFAST_CUDA_GRAPHS", "1") not in ("0", "false", "off")
+
+
+def _max_batch() -> int:
+    return int(os.environ.get("HAIRFAST_GRAPH_MAX_BATCH", "8"))
+
+
+def stats() -> dict:
+    return dict(_STATS)
+
+
+def _flatten(out, acc):
+    if torch.is_tensor(out):
+        acc.append(out)
+        return ("t", len(acc) - 1)
+    if isinstance(out, (list, tuple)):
+        return ("l" if isinstance(out, list) else "u", [_flatten(o, acc) for o in out])
+    return ("c", out)
+
+
+def _rebuild(spec, tensors):
+    kind, val = spec
+    if kind == "t":
+        return tensors[val].clone()
+    if kind == "c":
+        return val
+    seq = [_rebuild(s, tensors) for s in val]
+    return seq if kind == "l" else tuple(seq)
+
+
+class _Entry:
+    __slots__ = ("graph", "static_in", "outs", "spec", "pack_key")
+
+
+def _capture(fn, x, pack_key):
+    ent = _Entry()
+    ent.pack_key = pack_key
+    ent.static_in = x.clone()
+    cur = torch.cuda.current_stream(x.device)
+    side = torch.cuda.Stream(device=x.device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):                       # warm-up on a side stream (PyTorch's capture recipe)
+        fn(ent.static_in)
+    cur.wait_stream(side)
+    torch.cuda.synchronize(x.device)
+    ent.graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(ent.graph):
+        out = fn(ent.static_in)
+    ent.outs = []
+    ent.spec = _flatten(out, ent.outs)
+    return ent
+
+
+def run(owner, tag: str, pack_key, fn, x: torch.Tensor):
+    """`fn(x)` -- eagerly the first time a signature is seen, captured on the second, replayed afterwards."""
+    if (not enabled() or not x.is_cuda or x.dim() < 1 or x.shape[0] > _max_batch()
+            or torch.cuda.is_current_stream_capturing()):
+        _STATS["eager"] += 1
+        return fn(x)
+    cache = owner.__dict__.setdefault("_hf_graphs", {})
+    sig = (tag, tuple(x.shape), x.dtype, x.device.index)
+    ent = cache.get(sig)
+    if isinstance(ent, _Entry) and ent.pack_key != pack_key:
+        ent = None                                      # weights changed: drop the stale graph
+        cache.pop(sig, None)
+    if ent is None:                                     # first sighting: eager (packs weights, sets kernel attributes)
+        cache[sig] = 1
+        _STATS["eager"] += 1
+        return fn(x)
+    if ent is False:
+        _STATS["eager"] += 1
+        return fn(x)
+    if ent == 1:
+        try:
+            ent = cache[sig] = _capture(fn, x.contiguous(), pack_key)
+            _STATS["captures"] += 1
+        except Exception:                               # noqa: BLE001 -- not capturable here: stay eager for this signature
+            cache[sig] = False
+            _STATS["failed"] += 1
+            torch.cuda.synchronize(x.device)
+            return fn(x)
+    ent.static_in.copy_(x)
+    ent.graph.replay()
+    _STATS["replays"] += 1
+    return _rebuild(ent.spec, ent.outs)

@@ -29,6 +29,10 @@ After ``install()`` the import statements of the reference resolve to this packa
 * ``from utils.image_utils import DilateErosion`` (models/Alignment.py:11, models/Blending.py:7): the name is rebound
   inside ``utils.image_utils`` after import                                         -> ``hairfastgan_b200.masks``
 
+* ``FaceParsing_tensor.parsing_img`` (face_parsing/my_parsing_util.py:70-89) is wrapped after import: same labels from
+  ``BiSeNet.parse_labels`` without the full-resolution logits (``install(fuse_face_parsing=False)`` to keep it)
+                                                                                    -> ``hairfastgan_b200.parsing_fast``
+
 Nothing in the reference tree is edited and its JIT build of the two 2019 CUDA extensions
 (op/fused_act.py:10-16, op/upfirdn2d.py:10-16) never runs.
 """
@@ -81,11 +85,19 @@ _saved_attrs = []
 # FeatureStyleEncoder/FSencoder.py:12-19 puts its directory on sys.path and does `from trainer import *`; with
 # install(skip_fse_reconstruction=True) Trainer.test gets the fast path of hairfastgan_b200/fse_fast.py
 _FSE_TRAINER = "trainer"
+# face parsing: FaceParsing_tensor.parsing_img (my_parsing_util.py:70-89) -> label-only path of hairfastgan_b200/parsing_fast.py
+_PARSING_UTIL = "models.CtrlHair.external_code.face_parsing.my_parsing_util"
+_patched_parsing = []
 _post_import = set()          # module names the meta-path hook currently patches
 _patched_trainers = []
 
 
 def _patch_postprocess(module) -> None:
+    if module.__name__ == _PARSING_UTIL:
+        fast = importlib.import_module("hairfastgan_b200.parsing_fast")
+        if fast.patch_parsing_module(module):
+            _patched_parsing.append(module)
+        return
     if module.__name__ == _FSE_TRAINER:
         fast = importlib.import_module("hairfastgan_b200.fse_fast")
         if fast.patch_trainer_module(module):
@@ -152,7 +164,7 @@ def _register(ref_name: str, ours: str) -> None:
 
 
 def install(generator: bool = True, encoders: bool = True, postprocess: bool = True, segmentation: bool = True,
-            glue: bool = True, skip_fse_reconstruction: bool = False) -> None:
+            glue: bool = True, skip_fse_reconstruction: bool = False, fuse_face_parsing: bool = True) -> None:
     """Register the overlay.  ``generator=False`` swaps only the operator package (L1 boundary) and leaves the
     reference's own ``models/stylegan2/model.py`` classes in place on top of our ops; ``encoders=False`` keeps
     the reference's PyTorch encoders; ``postprocess=False`` keeps its PostProcess conv stack; ``segmentation=False``
@@ -175,6 +187,9 @@ def install(generator: bool = True, encoders: bool = True, postprocess: bool = T
         _post_import.update(_POSTPROCESS)
     if glue:
         _post_import.update(_GLUE_ATTRS)
+    if segmentation and fuse_face_parsing:
+        # label-only face parsing (bit-identical labels, no full-resolution logits): hairfastgan_b200/parsing_fast.py
+        _post_import.add(_PARSING_UTIL)
     if skip_fse_reconstruction:
         # opt-in: Trainer.test(img=..., return_latent=True) skips the StyleGAN reconstruction whose image swap() never
         # reads (x_1_recon comes back as None) and draws the same noise, so later random numbers are unchanged
@@ -199,4 +214,7 @@ def uninstall() -> None:
     for module in _patched_trainers:
         importlib.import_module("hairfastgan_b200.fse_fast").unpatch_trainer_module(module)
     _patched_trainers.clear()
+    for module in _patched_parsing:
+        importlib.import_module("hairfastgan_b200.parsing_fast").unpatch_parsing_module(module)
+    _patched_parsing.clear()
     _post_import.clear()

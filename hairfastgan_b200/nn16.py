@@ -250,3 +250,13 @@ def bilinear_upsample_nchw(x: torch.Tensor, channels: int, height: int, width: i
     _lib.check(_lib.lib().hf_bilinear_upsample_nchw_f32(x.data_ptr(), y.data_ptr(), b, channels, cin, h, w, height, width,
                                                         _lib.stream_ptr()), "hf_bilinear_upsample_nchw_f32")
     return y
+
+
+def bilinear_argmax_nchw(x: torch.Tensor, channels: int, height: int, width: int):
+    """argmax over the first `channels` planes of F.interpolate(x, (height, width), 'bilinear', align_corners=True):
+    int64 labels [B, height, width]; the full-resolution logits are never written."""
+    b, cin, h, w = x.shape
+    y = torch.empty(b, height, width, device=x.device, dtype=torch.int64)
+    _lib.check(_lib.lib().hf_bilinear_argmax_nchw_f32(x.data_ptr(), y.data_ptr(), b, channels, cin, h, w, height, width,
+                                                      _lib.stream_ptr()), "hf_bilinear_argmax_nchw_f32")
+    return y

@@ -19,8 +19,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import nn16
-from .encoders import IBasicBlock, _params_key, fs_encoder_v2
+from . import graphs, nn16
+from .encoders import IBasicBlock, _PackCacheMixin, _params_key, fs_encoder_v2
 
 __all__ = ["FeatureEncoder", "FeatureEncoderMult", "FeatureiResnet", "IBasicBlock", "conv1x1", "conv3x3",
            "transform_to_256"]
@@ -93,10 +93,10 @@ class FeatureEncoderMult(FeatureEncoder):
 
     @torch.no_grad()
     def forward(self, x):
-        return self._trunk(transform_to_256(x))
+        return self._graphed_trunk(transform_to_256(x))
 
 
-class FeatureiResnet(nn.Module):
+class FeatureiResnet(_PackCacheMixin, nn.Module):
     """models/Encoders.py:35-57."""
 
     def __init__(self, blocks, inplanes=1024):
@@ -124,6 +124,9 @@ class FeatureiResnet(nn.Module):
             raise RuntimeError("FeatureiResnet: only eval-mode (running BatchNorm statistics) forward is implemented")
         if not x.is_cuda:
             raise RuntimeError("FeatureiResnet: input must be a CUDA tensor (no CPU fallback)")
+        return graphs.run(self, "res", _params_key(self), self._forward_impl, x)
+
+    def _forward_impl(self, x):
         blocks = self._pack()
         # x is fp32 NCHW (torch.cat of the two content maps); the first block's BatchNorm rides on the layout change
         raw = nn16.to_nhwc16(x)

@@ -283,6 +283,13 @@ int hf_gate_add_up_nhwc16(const void* x16, const float* gate, const float* addve
 int hf_bilinear_upsample_nchw_f32(const float* x, float* y, int batch, int channels, int in_channels, int h, int w,
                                   int height, int width, void* stream);
 
+/* Fused upsample + arg-max for face parsing: labels[b,Y,X] = argmax_c of the bilinear (align_corners=True)
+ * interpolation of x[b,c] to (height, width) -- BiSeNet.forward's F.interpolate (face_parsing/model.py:239) followed
+ * by `out.squeeze(0).argmax(0)` (face_parsing/my_parsing_util.py:87-88).  Same arithmetic as
+ * hf_bilinear_upsample_nchw_f32, first maximum wins (torch.argmax).  labels: int64 [B,height,width]. */
+int hf_bilinear_argmax_nchw_f32(const float* x, long long* labels, int batch, int channels, int in_channels, int h,
+                                int w, int height, int width, void* stream);
+
 /* ---- stage glue ---- */
 /* BicubicDownSample.forward (utils/bicubic.py:36-78): reflect-pad + separable `4*factor`-tap FIR + decimation by
  * `factor`, vertical pass first.  x [planes,H,W] -> y [planes,H/factor,W/factor] fp32; kernel [4*factor] = the
@@ -296,6 +303,21 @@ int hf_bicubic_downsample_f32(const float* x, const float* kernel, float* y, int
  * workspace: 4 * planes * H * W floats (unused when iterations <= 1). */
 int hf_dilate_erode_f32(const float* mask, float* dilate, float* erode, void* workspace, int planes, int height,
                         int width, int iterations, void* stream);
+
+/* Mask algebra of the F-space alignment (models/Alignment.py:139-143): from the three 0/1 hair masks [n] each,
+ * masks = [1 - (1 - hm1)(1 - hmx), hmx, hm2 * hmx] -> `masks` [3, n] fp32 (the input of DilateErosion.mask, :145). */
+int hf_align_masks_f32(const float* hair_mask1, const float* hair_mask2, const float* hair_mask_target, float* masks,
+                       int n, void* stream);
+
+/* F-space blend chain (models/Alignment.py:153-159; with one stage: the Embedding mixing, models/Embedding.py:86-92):
+ *   w_s = scale_a[s] + scale_b[s] * F.interpolate(mask[s] [mask_height, mask_width], size=(height, width), 'bicubic')
+ *   F   = src[s] + w_s * (F - src[s])   for s = 0 .. n_stage-1, F starting from `first`
+ * first, src[s], out: [channels, height, width] fp32; w_s broadcasts over channels; src / mask are HOST arrays of
+ * n_stage device pointers, scale_a / scale_b HOST arrays of n_stage floats (1 <= n_stage <= 4).  Alignment uses
+ * (scale_a, scale_b) = (1, -1) (`interpolation_low = 1 - free_mask_down_32`), Embedding (0, opts.mixing). */
+int hf_fspace_blend_f32(const float* first, const float* const* src, const float* const* mask, const float* scale_a,
+                        const float* scale_b, float* out, int n_stage, int channels, int height, int width,
+                        int mask_height, int mask_width, void* stream);
 
 /* Number of kernels the last hf_generator_forward / hf_conv_forward of this thread launched. */
 int hf_last_launch_count(void);

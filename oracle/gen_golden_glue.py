@@ -62,6 +62,52 @@ def main():
     out["labels"] = labels.numpy().astype(np.uint8)
     out["hair_dilate"] = d.numpy().astype(np.uint8)
     out["hair_erode"] = e.numpy().astype(np.uint8)
+    # ---- F-space alignment: run the reference's OWN source lines (models/Alignment.py:139-159, the body of
+    # align_images between the SEAN re-encoding and the save_all block) on synthetic inputs.  Nothing is copied into the
+    # repo: the text is read from the checkout here, dedented and exec'd with the names it uses.
+    import textwrap
+    import torch.nn.functional as F
+    src = open(os.path.join(REF, "models", "Alignment.py")).read().split("\n")
+    block = textwrap.dedent("\n".join(src[138:159]))                 # lines 139..159 (1-based)
+    assert block.lstrip().startswith("masks = [") and "latent_F_align = latent_F_2" in block, block[:200]
+    gm = torch.Generator().manual_seed(64)
+
+    def blob(seed_shift):
+        return (torch.nn.functional.avg_pool2d(torch.rand(1, 1, 256, 256, generator=gm), 15, 1, 7) > 0.5).float()
+    ns = {"torch": torch, "F": F, "hair_mask1": blob(0), "hair_mask2": blob(1), "hair_mask_target": blob(2),
+          "self": types.SimpleNamespace(dilate_erosion=DilateErosion(dilate_erosion=5, device="cpu"))}
+    for name in ("intermediate_align", "latent_F_1", "latent_F_out_new", "latent_F_2"):
+        ns[name] = torch.randn(1, 64, 32, 32, generator=gm)
+    inputs = {k: ns[k].clone() for k in ("hair_mask1", "hair_mask2", "hair_mask_target", "intermediate_align",
+                                         "latent_F_1", "latent_F_out_new", "latent_F_2")}
+    exec(block, ns)
+    mo = GO.align_masks_ref(inputs["hair_mask1"], inputs["hair_mask2"], inputs["hair_mask_target"])
+    fo = GO.align_f_space_ref(inputs["intermediate_align"], inputs["latent_F_1"], inputs["latent_F_out_new"],
+                              inputs["latent_F_2"], ns["free_mask"])
+    print("align masks: ref vs oracle mismatches", int((ns["masks"] != mo).sum()),
+          "| latent_F_align ref vs oracle max abs", float((ns["latent_F_align"] - fo).abs().max()))
+    for k, v in inputs.items():
+        out["fs_" + k] = v.numpy()
+    out["fs_masks"] = ns["masks"].numpy().astype(np.uint8)
+    out["fs_free_mask"] = ns["free_mask"].numpy().astype(np.uint8)
+    out["fs_latent_F_align"] = ns["latent_F_align"].numpy()
+    # Embedding mixing (models/Embedding.py:86-92): the three statements inside `if len(images_to_name) > 1:`
+    esrc = open(os.path.join(REF, "models", "Embedding.py")).read().split("\n")
+    eblock = textwrap.dedent("\n".join(esrc[85:88]) + "\n" + esrc[91])       # lines 86-88 and 92 (1-based)
+    assert "hair_mask = torch.where(masks == 13" in eblock and "latent_F = latent_F + self.opts.mixing" in eblock, eblock
+    labels = torch.randint(10, 16, (2, 1, 256, 256), generator=gm)
+    labels = torch.nn.functional.interpolate(labels[:, :, ::16, ::16].float(), size=(256, 256), mode="nearest").long()
+    ens = {"torch": torch, "F": F, "masks": labels, "device": "cpu",
+           "latent_F": torch.randn(2, 64, 32, 32, generator=gm), "latent_F_from_W": torch.randn(2, 64, 32, 32, generator=gm),
+           "self": types.SimpleNamespace(opts=types.SimpleNamespace(mixing=0.95))}
+    out["mix_labels"] = labels.numpy().astype(np.uint8)
+    out["mix_latent_F"] = ens["latent_F"].numpy().copy()
+    out["mix_latent_F_from_W"] = ens["latent_F_from_W"].numpy()
+    lf0 = ens["latent_F"].clone()
+    exec(eblock, ens)
+    mo = GO.mix_f_space_ref(lf0, ens["latent_F_from_W"], labels, 0.95)
+    print("embedding mixing: ref vs oracle max abs", float((ens["latent_F"] - mo).abs().max()))
+    out["mix_out"] = ens["latent_F"].numpy()
     np.savez_compressed(os.path.join(GOLD, "glue.npz"), **out)
     print("glue.npz", {k: v.shape for k, v in out.items()})
 

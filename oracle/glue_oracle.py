@@ -66,3 +66,29 @@ def bicubic_downsample_ref(x: torch.Tensor, factor: int, clip_round: bool = Fals
     if clip_round:
         y = torch.clamp(torch.round(y.float()), 0.0, 255.0).double()
     return y.float()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# F-space alignment: models/Alignment.py:139-159 and the Embedding mixing models/Embedding.py:86-92.  These are inline
+# torch expressions in the reference; restated literally.  Pinned by tests/golden/glue.npz: gen_golden_glue.py EXECUTES
+# the reference's own source lines (read from the checkout at generation time) on the same inputs.
+# ---------------------------------------------------------------------------------------------------------------------
+def align_masks_ref(hair_mask1: torch.Tensor, hair_mask2: torch.Tensor, hair_mask_target: torch.Tensor) -> torch.Tensor:
+    """models/Alignment.py:139-144."""
+    return torch.cat([1 - (1 - hair_mask1) * (1 - hair_mask_target), hair_mask_target, hair_mask2 * hair_mask_target],
+                     dim=0)
+
+
+def align_f_space_ref(intermediate_align, latent_F_1, latent_F_out_new, latent_F_2, free_mask):
+    """models/Alignment.py:153-159 (free_mask = stack(dilate[0], erosion[1], erosion[2]), :147-152)."""
+    low = 1 - torch.nn.functional.interpolate(free_mask.float(), size=(32, 32), mode='bicubic')
+    f = intermediate_align + low[0] * (latent_F_1 - intermediate_align)
+    f = latent_F_out_new + low[1] * (f - latent_F_out_new)
+    return latent_F_2 + low[2] * (f - latent_F_2)
+
+
+def mix_f_space_ref(latent_F, latent_F_from_W, masks, mixing: float):
+    """models/Embedding.py:86-92 (masks = the [B,1,256,256] label maps)."""
+    hair = torch.where(masks == 13, torch.ones_like(masks), torch.zeros_like(masks))
+    hair = torch.nn.functional.interpolate(hair.float(), size=(32, 32), mode='bicubic')
+    return latent_F + mixing * hair * (latent_F_from_W - latent_F)

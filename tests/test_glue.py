@@ -84,3 +84,46 @@ def test_bicubic_downsample_gpu(golden_dir):
     yn = B.BicubicDownSample(factor=2)(xn.cuda(), nhwc=True).cpu()
     assert yn.shape == (1, 32, 48, 3)
     assert float((yn.permute(0, 3, 1, 2) - GO.bicubic_downsample_ref(big[:1, :, :64, :96], 2)).abs().max()) < 2e-6
+
+
+# ---- F-space alignment / Embedding mixing (models/Alignment.py:139-159, models/Embedding.py:86-92) --------------------
+def test_fspace_oracle_matches_reference_lines(golden_dir):
+    """The oracle restatement against the golden produced by EXECUTING the reference's own source lines."""
+    g = np.load(os.path.join(golden_dir, "glue.npz"))
+    t = {k: torch.from_numpy(g[k]) for k in g.files if k.startswith(("fs_", "mix_"))}
+    masks = GO.align_masks_ref(t["fs_hair_mask1"], t["fs_hair_mask2"], t["fs_hair_mask_target"])
+    assert torch.equal(masks, t["fs_masks"].float())
+    f = GO.align_f_space_ref(t["fs_intermediate_align"], t["fs_latent_F_1"], t["fs_latent_F_out_new"], t["fs_latent_F_2"],
+                             t["fs_free_mask"].float())
+    assert torch.equal(f, t["fs_latent_F_align"])
+    m = GO.mix_f_space_ref(t["mix_latent_F"], t["mix_latent_F_from_W"], t["mix_labels"].long(), 0.95)
+    assert torch.equal(m, t["mix_out"])
+
+
+@pytest.mark.gpu
+def test_fspace_kernels_gpu(golden_dir):
+    """hf_align_masks_f32 (bit-exact: 0/1 arithmetic) and hf_fspace_blend_f32 (<= 1e-6: fp32, fma contraction only)
+    against the reference-generated golden; plus a ragged size against the oracle."""
+    import hairfastgan_b200.fspace as FS
+    g = np.load(os.path.join(golden_dir, "glue.npz"))
+    t = {k: torch.from_numpy(g[k]).cuda() for k in g.files if k.startswith(("fs_", "mix_"))}
+    masks = FS.align_masks(t["fs_hair_mask1"], t["fs_hair_mask2"], t["fs_hair_mask_target"])
+    assert torch.equal(masks.cpu(), torch.from_numpy(g["fs_masks"]).float())
+    f = FS.align_f_space(t["fs_intermediate_align"], t["fs_latent_F_1"], t["fs_latent_F_out_new"], t["fs_latent_F_2"],
+                         t["fs_free_mask"].float())
+    err = float((f.cpu() - torch.from_numpy(g["fs_latent_F_align"])).abs().max())
+    assert f.shape == (1, 64, 32, 32) and err <= 2e-6, err
+    hair = (t["mix_labels"] == 13).float()
+    for b in range(2):
+        m = FS.mix_f_space(t["mix_latent_F"][b:b + 1], t["mix_latent_F_from_W"][b:b + 1], hair[b], 0.95)
+        e = float((m.cpu()[0] - torch.from_numpy(g["mix_out"])[b]).abs().max())
+        assert e <= 2e-6, e
+    # ragged: 3 channels, 20x12 output from a 50x70 mask (clamped taps at the borders, scalar tail path)
+    gen = torch.Generator().manual_seed(5)
+    a, b2 = torch.randn(1, 3, 20, 12, generator=gen), torch.randn(1, 3, 20, 12, generator=gen)
+    mk = torch.rand(1, 1, 50, 70, generator=gen)
+    want = b2 + (1 - torch.nn.functional.interpolate(mk, size=(20, 12), mode="bicubic")) * (a - b2)
+    got = FS.fspace_blend(a.cuda(), [(b2.cuda(), mk.cuda(), 1.0, -1.0)])
+    assert float((got.cpu() - want).abs().max()) <= 2e-6
+    with pytest.raises(RuntimeError):
+        FS.align_masks(t["fs_hair_mask1"].cpu(), t["fs_hair_mask2"].cpu(), t["fs_hair_mask_target"].cpu())

@@ -217,6 +217,12 @@ def test_bisenet_golden(N, golden_dir):
     agree = float((out[:, :, ::4, ::4].cpu().argmax(1) == ref_label).float().mean())
     record("bisenet_argmax_agreement", agreement=agree)
     assert agree > 0.97
+    # label-only path (parsing_fast.py): bit-identical to the arg-max of the full forward, also on a non-square size
+    labels = net.parse_labels(x.cuda())
+    assert labels.dtype == torch.int64 and labels.shape == (2, 256, 256)
+    assert torch.equal(labels, out.argmax(1))
+    x2 = torch.rand(1, 3, 128, 320, generator=torch.Generator().manual_seed(53)).cuda() * 2 - 1
+    assert torch.equal(net.parse_labels(x2), net(x2)[0].argmax(1))
 
 
 def test_config4_inversion_batch32(N):
@@ -249,3 +255,43 @@ def test_config4_inversion_batch32(N):
     e1, e2 = rel_err(lat32[30:32], lo)[0], rel_err(c32[30:32], co)[0]
     record("fse_b32_tail_vs_oracle", latent_rel_max_err=e1, content_rel_max_err=e2)
     assert e1 < TOL_ENC[dtype_name()] and e2 < TOL_ENC_MAP_B32[dtype_name()], (e1, e2)
+
+
+def test_cuda_graph_replay_matches_eager(N):
+    """graphs.py: call 1 eager, call 2 captures, call 3+ replay -- bit-identical outputs every time; a weight change
+    recaptures; HAIRFAST_CUDA_GRAPHS=0 keeps everything eager; batches above the cap stay eager."""
+    import hairfastgan_b200.encoders as E
+    import hairfastgan_b200.bisenet as B
+    from hairfastgan_b200 import graphs
+    x = (torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(90)) * 2 - 1).cuda()
+    e4e = E.Encoder4Editing(50, "ir_se", types.SimpleNamespace(stylegan_size=1024)).eval()
+    e4e.load_state_dict(EO.synth_params_like(e4e, seed=11), strict=True)
+    e4e = e4e.cuda()
+    s0 = graphs.stats()
+    outs = [e4e(x).clone() for _ in range(4)]
+    s1 = graphs.stats()
+    assert s1["captures"] == s0["captures"] + 1 and s1["replays"] >= s0["replays"] + 3 and s1["failed"] == s0["failed"]
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+    os.environ["HAIRFAST_CUDA_GRAPHS"] = "0"
+    try:
+        assert torch.equal(e4e(x), outs[0])                      # eager result == replayed result
+    finally:
+        os.environ.pop("HAIRFAST_CUDA_GRAPHS")
+    y2 = (torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(91)) * 2 - 1).cuda()
+    r2 = e4e(y2)                                                 # same signature, new data: replay with fresh input
+    assert not torch.equal(r2, outs[0]) and torch.equal(r2, e4e(y2))
+    e4e.load_state_dict(EO.synth_params_like(e4e, seed=12), strict=True)     # in-place copy: version key changes
+    a = e4e(x)
+    assert not torch.equal(a, outs[0])
+    assert torch.equal(a, e4e(x)) and torch.equal(a, e4e(x))
+    # tuple / list outputs (FS encoder) and the label path of BiSeNet
+    fse = E.fs_encoder_v2(n_styles=18, opts=None, stride=(2, 2)).eval()
+    fse.load_state_dict(EO.synth_params_like(fse, seed=21), strict=True)
+    fse = fse.cuda()
+    f = [fse(x) for _ in range(3)]
+    assert all(torch.equal(f[0][0], o[0]) and torch.equal(f[0][1], o[1]) for o in f[1:])
+    seg = B.BiSeNet(n_classes=19).eval()
+    seg.load_state_dict(EO.synth_params_like(seg, seed=51), strict=True)
+    seg = seg.cuda()
+    lab = [seg.parse_labels(x[:1]) for _ in range(3)]
+    assert all(torch.equal(lab[0], o) for o in lab[1:]) and torch.equal(lab[0], seg(x[:1])[0].argmax(1))

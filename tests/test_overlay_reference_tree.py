@@ -56,6 +56,7 @@ PROBE = textwrap.dedent("""
         "trainer.fs_encoder_v2": trainer.fs_encoder_v2.__module__,
         "trainer.Trainer.test": "patched" if hasattr(trainer.Trainer.test, "__wrapped__") else "reference",
         "parsing.BiSeNet": parsing.BiSeNet.__module__,
+        "parsing.parsing_img": "patched" if hasattr(parsing.FaceParsing_tensor.parsing_img, "__wrapped__") else "reference",
         "Net.Net": net.Net.__module__,
     }
     for k, v in got.items():
@@ -76,6 +77,7 @@ EXPECTED = {
     "trainer.fs_encoder_v2": "hairfastgan_b200.encoders",
     "trainer.Trainer.test": "patched",
     "parsing.BiSeNet": "hairfastgan_b200.bisenet",
+    "parsing.parsing_img": "patched",
     "Net.Net": "models.Net",                      # the orchestration class stays the reference's
 }
 
