@@ -134,7 +134,7 @@ def main():
     os.makedirs(work, exist_ok=True)
     refenv.activate(overlay=False, chdir=False)
     import torch
-    threads = a.threads or os.cpu_count()
+    threads = a.threads or os.cpu_count()            # bench.py passes the physical core count
     torch.set_num_threads(threads)                  # torchrun exports OMP_NUM_THREADS=1: do not inherit it silently
     dev = torch.device(a.device)
     nets = build(dev, work)

@@ -183,7 +183,7 @@ def run_ours(args, rank, world, local_rank):
     host_out = torch.empty(T, 3, 1024, 1024).pin_memory()
     launches = [0]
 
-    def compute(inp, skip_fse_recon=False):
+    def compute(inp, skip_fse_recon=False, full_seg=False):
         """The hot path of T triples through the public module API (what swap()'s stages call)."""
         img, lats, lins, calls = inp["img"], inp["lat"], inp["lin"], inp["calls"]
         n0 = lib.hf_total_launch_count()
@@ -200,8 +200,12 @@ def run_ours(args, rank, world, local_rank):
         _, (f_face,) = pp_enc(img[3])                  # PostProcessModel.forward, models/Encoders.py:120-139
         _, (f_hair,) = pp_enc(img[4])
         pp_res(torch.cat((f_face, f_hair), dim=1))
-        seg(img[5])                                    # get_segmentation x3 at 512^2 (models/Net.py:108-115)
-        seg(img[6]); seg(img[6])                       # and twice at 1024^2
+        # get_segmentation x3 at 512^2 and twice at 1024^2 (models/Net.py:108-115).  Under install()'s defaults the
+        # reference's FaceParsing_tensor.parsing_img runs the label-only path (parsing_fast.py: bit-identical labels,
+        # aux heads + full-resolution logits not materialised); `full_seg=True` = the module's three-logit forward
+        parse = seg if full_seg else seg.parse_labels
+        parse(img[5])
+        parse(img[6]); parse(img[6])
         launches[0] += lib.hf_total_launch_count() - n0
         return final
 
@@ -358,6 +362,11 @@ def run_ours(args, rank, world, local_rank):
         extra["fse_recon_skipped"] = {"value": round(T / (ms_skip * 1e-3), 3), "unit": "triples/s",
                                       "ms_per_step": round(ms_skip, 3),
                                       "note": "same outputs for swap(); not the default, see INTEGRATION.md"}
+        ms_full = avg_ms(lambda: compute(devin, full_seg=True))
+        extra["bisenet_full_logits_step"] = {"value": round(T / (ms_full * 1e-3), 3), "unit": "triples/s",
+                                             "ms_per_step": round(ms_full, 3),
+                                             "note": "the step with BiSeNet.forward's three [B,19,H,W] fp32 logit "
+                                                     "outputs instead of the label-only path install() uses"}
         # configs[1]: full 1024^2 generator forward, B=4
         lat4 = torch.randn(4, 18, 512, device=dev)
         us_img = avg_ms(lambda: gen([lat4], input_is_latent=True)) / 4 * 1e3
@@ -538,9 +547,20 @@ CPU_SAMPLE = ("every distinct call of the SURVEY App. B census once at B=1 (gene
 
 
 def cpu_threads():
-    """All host cores, stated.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must not inherit that
-    silently (round 1: 64 threads at N=1, 1 thread under torchrun -> a 4.5x swing of the denominator)."""
-    return os.cpu_count() or 1
+    """Physical host cores, stated.  torchrun exports OMP_NUM_THREADS=1 to its workers (round 1: 64 threads at N=1, one
+    thread under torchrun -> a 4.5x swing of the denominator), and os.cpu_count() counts hyper-threads (128 on the B200
+    hosts: measured 40x SLOWER than 64 threads on these B=1 convolutions), so neither is inherited silently."""
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+    except Exception:   # noqa: BLE001
+        n = None
+    n = n or os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    return max(1, n)
 
 
 def cpu_census_reference(steps: int, warmup: int):
@@ -663,8 +683,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = ("SURVEY-8 hot path of HairFast.swap(): 8 Generator.forward calls (1024^2, randomize_noise=True) + "
                 "e4e on 5 and FSE on 3 images (256^2) + PostProcess conv stack (FeatureEncoderMult x2, FeatureiResnet "
-                "@64^2) + BiSeNet on 3 images at 512^2 and 2 at 1024^2 per triple = 3063.8 GFLOP/triple (SURVEY "
-                "App. B / 8d config 3 / 8f-3), synthetic weights; out-of-scope nets (SEAN/CLIP/mask) and stage glue "
+                "@64^2) + BiSeNet face parsing (labels, as install() runs it) on 3 images at 512^2 and 2 at 1024^2 "
+                "per triple = 3063.8 GFLOP/triple in the reference's formulation (SURVEY App. B / 8d config 3 / 8f-3), "
+                "synthetic weights; out-of-scope nets (SEAN/CLIP/mask) and stage glue "
                 "excluded")
     global WORKLOAD
     WORKLOAD = workload
@@ -714,7 +735,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         s_per_triple, thr, kind, per_call = cpu_census(1, 0)
         out["cpu_baseline"] = {"value": round(1.0 / s_per_triple, 5), "unit": "triples/s", "cores": thr, "kind": kind,
-                               "sample": f"{s_per_triple:.1f} s per triple: " + CPU_SAMPLE}
+                               "sample": f"{s_per_triple:.1f} s per triple: " + CPU_SAMPLE, "per_call_s": per_call}
     emit(out)
 
 

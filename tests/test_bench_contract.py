@@ -36,7 +36,7 @@ def test_reference_arm_line(arm):
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and d["gpu_launches"] == 0
     assert d["e2e"] == {"value": d["value"], "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
-    assert cb["kind"] == arm and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and "sample" in cb
+    assert cb["kind"] == arm and cb["cores"] > 1 and cb["value"] == d["value"] and "sample" in cb
     assert "workload" in d["config"] and set(cb["per_call_s"]) >= {"gen_full", "e4e", "seg_1024"}
 
 

@@ -135,8 +135,8 @@ def test_generator1024_golden_and_batch_properties(M, golden_dir):
 
 
 # north_star: "max-abs on generator RGB".  Stated ABSOLUTE tolerance on a unit-range image (RGB in [-1, 1], what a
-# trained generator emits): bf16 operands 2e-2, fp16 operands 3e-3.
-TOL_RGB_ABS_UNIT = {"bf16": 2e-2, "fp16": 3e-3}
+# trained generator emits): bf16 operands 1.5e-2, fp16 operands 2e-3 (measured on B200: 8.2e-3 / 7.0e-4).
+TOL_RGB_ABS_UNIT = {"bf16": 1.5e-2, "fp16": 2e-3}
 
 
 def test_generator1024_unit_range_rgb_max_abs(M, golden_dir):

@@ -30,10 +30,11 @@ HF_DTYPES = ["default", "fp16"]
 # seeds.  The pipeline has discrete decisions (BiSeNet arg-max labels -> 256^2 masks -> F-space blends), so a small set
 # of pixels near label boundaries can move by more than the arithmetic error; the bound is therefore on the mean and on
 # a high quantile, with the max reported.
-# Measured on B200 (round 2): all-bf16 mean 1.7e-4 / q99 5.8e-4 / max 1.6e-3.
-TOL_FINAL_MEAN = {"default": 1e-3, "bf16": 1e-3, "fp16": 3e-4}
-TOL_FINAL_Q99 = {"default": 4e-3, "bf16": 4e-3, "fp16": 1.2e-3}
-TOL_FINAL_MAX = {"default": 2e-2, "bf16": 2e-2, "fp16": 1e-2}
+# Measured on B200 (round 2), mean / q99 / max: all-bf16 1.7e-4 / 5.8e-4 / 1.6e-3; default (generator bf16, encoders
+# fp16) 9.6e-5 / 3.3e-4 / 8.5e-4; all-fp16 3.0e-5 / 1.2e-4 / 4.0e-4.  Stated bounds = ~4x the measurement.
+TOL_FINAL_MEAN = {"default": 4e-4, "bf16": 8e-4, "fp16": 1.5e-4}
+TOL_FINAL_Q99 = {"default": 1.5e-3, "bf16": 2.5e-3, "fp16": 5e-4}
+TOL_FINAL_MAX = {"default": 5e-3, "bf16": 8e-3, "fp16": 2e-3}
 _reference_arm = {}
 
 
