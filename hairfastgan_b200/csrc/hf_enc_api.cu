@@ -125,6 +125,13 @@ int hf_adaptive_avgpool_nhwc16(const void* x16, float* y, int batch, int height,
 }
 
 /* ---- BiSeNet glue ---- */
+int hf_stem7x7s2_nhwc16(const float* x, const void* wpacked, const float* shift, void* y16, int batch, int height,
+                        int width, int dtype, void* stream) {
+  int rc = ensure_device_current();
+  if (rc) return rc;
+  return launch_stem7x7s2_fused(x, wpacked, shift, y16, batch, height, width, dtype, (cudaStream_t)stream);
+}
+
 int hf_im2col7x7s2_nhwc16(const float* x, void* y16, int batch, int height, int width, int dtype, void* stream) {
   int rc = ensure_device_current();
   if (rc) return rc;

@@ -256,6 +256,137 @@ int launch_gate_add_up(const void* x16, const float* gate, const float* addvec, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused stem (round 2): Resnet18.conv1 7x7/s2/p3 + bn1 + ReLU (resnet.py:60-61,69-70) in ONE kernel, fp32 NCHW image in,
+// 16-bit NHWC [B,Ho,Wo,64] out -- the [B,Ho,Wo,160] im2col tensor (21 MB per 512^2 image, written by one kernel and
+// read back by the next: 0.84 ms of a B=48 call) no longer exists.
+// Roofline: 1.23 GFLOP against 3 MB in + 8.4 MB out per 512^2 image = 108 FLOP/B, far left of the ridge (~260): the
+// kernel is HBM-bound, so the contraction runs on warp-level mma.sync.m16n8k16 fragments built straight from a
+// shared-memory copy of the input window (K = 7 rows x 24 [= 7 taps x 3 channels + 3 zero-weight pads] = 168 -> 176);
+// a tcgen05 tile would need the same im2col rows materialised in the swizzled UMMA layout first.
+// CTA = 8 x 32 output pixels x 64 channels, 8 warps (one output row each: 2 m16 tiles x 8 n8 tiles x 11 k16 steps).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSfRows = 8, kSfCols = 32;                 // output tile
+constexpr int kSfInRows = 2 * kSfRows + 6;               // 22 (one spare row for the zero-weight K padding)
+constexpr int kSfInPitch = 216;                          // (2*32 + 8) * 3 interleaved [x][c] 16-bit elements
+constexpr int kSfK = 176, kSfWPitch = 184;               // packed weight row: [n][k], k = ky*24 + kx*3 + c
+
+template <int DT>
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  if (DT == HF_BF16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256, 2) stem7x7s2_fused_kernel(const float* __restrict__ x,
+                                                                 const uint16_t* __restrict__ wp,
+                                                                 const float* __restrict__ shift,
+                                                                 uint16_t* __restrict__ y, int H, int W, int Ho, int Wo) {
+  // [input window | weights]; after the MMA loop the same bytes are the swizzled 256 x 64 output staging tile
+  __shared__ __align__(16) uint16_t sm[kSfInRows * kSfInPitch + 64 * kSfWPitch];
+  uint16_t* in_s = sm;
+  uint16_t* w_s = sm + kSfInRows * kSfInPitch;
+  const int b = blockIdx.z, oy0 = blockIdx.y * kSfRows, ox0 = blockIdx.x * kSfCols;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* xb = x + (size_t)b * 3 * H * W;
+  // ---- stage the 22 x 72 x 3 input window (zero outside the image = the conv padding), interleaved [row][x*3 + c]
+  const int gy0 = 2 * oy0 - 3, gx0 = 2 * ox0 - 3;
+  for (int i = threadIdx.x; i < 3 * kSfInRows * 72; i += 256) {
+    const int cx = i % 72, t = i / 72, r = t % kSfInRows, c = t / kSfInRows;
+    const int gy = gy0 + r, gx = gx0 + cx;
+    const float v = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(xb + ((size_t)c * H + gy) * W + gx) : 0.f;
+    in_s[r * kSfInPitch + cx * 3 + c] = Half2T<DT>::one(v);
+  }
+  for (int i = threadIdx.x; i < 64 * kSfWPitch / 8; i += 256)
+    reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(wp) + i);
+  __syncthreads();
+
+  float acc[2][8][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+  const int g4 = lane >> 2, q2 = (lane & 3) * 2;
+  // A[pixel (warp, ox)][k = ky*24 + t] = in_s[2*warp + ky][6*ox + t]
+  const uint16_t* a_row = in_s + (2 * warp) * kSfInPitch;
+#pragma unroll
+  for (int ks = 0; ks < kSfK / 16; ++ks) {
+    int off[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int kk = ks * 16 + 8 * j + q2;
+      off[j] = (kk / 24) * kSfInPitch + (kk % 24);
+    }
+    uint32_t a[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int oxa = i * 16 + g4;
+      a[i][0] = *reinterpret_cast<const uint32_t*>(a_row + 6 * oxa + off[0]);
+      a[i][1] = *reinterpret_cast<const uint32_t*>(a_row + 6 * (oxa + 8) + off[0]);
+      a[i][2] = *reinterpret_cast<const uint32_t*>(a_row + 6 * oxa + off[1]);
+      a[i][3] = *reinterpret_cast<const uint32_t*>(a_row + 6 * (oxa + 8) + off[1]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t bf[2];
+      const uint16_t* wrow = w_s + (j * 8 + g4) * kSfWPitch + ks * 16 + q2;
+      bf[0] = *reinterpret_cast<const uint32_t*>(wrow);
+      bf[1] = *reinterpret_cast<const uint32_t*>(wrow + 8);
+      mma16816<DT>(acc[0][j], a[0], bf);
+      mma16816<DT>(acc[1][j], a[1], bf);
+    }
+  }
+  __syncthreads();                                       // everyone is done with in_s / w_s: reuse as output staging
+  // ---- epilogue: + shift (BatchNorm folded: scale lives in the weights), ReLU, 16-bit, swizzled staging
+  uint16_t* out_s = sm;                                  // [256 pixels][64 ch], 16-byte chunk index ^ (pixel & 7)
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s0 = __ldg(shift + j * 8 + q2), s1 = __ldg(shift + j * 8 + q2 + 1);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int pix = warp * 32 + i * 16 + g4 + 8 * h;
+        const float v0 = fmaxf(acc[i][j][2 * h] + s0, 0.f), v1 = fmaxf(acc[i][j][2 * h + 1] + s1, 0.f);
+        *reinterpret_cast<uint32_t*>(out_s + pix * 64 + ((j ^ (pix & 7)) * 8) + q2) = Half2T<DT>::pack(v0, v1);
+      }
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 256 * 8; i += 256) {
+    const int pix = i >> 3, ch = i & 7;
+    const int oy = oy0 + (pix >> 5), ox = ox0 + (pix & 31);
+    if (oy < Ho && ox < Wo) {
+      const uint4 v = *reinterpret_cast<const uint4*>(out_s + pix * 64 + ((ch ^ (pix & 7)) * 8));
+      *reinterpret_cast<uint4*>(y + (((size_t)b * Ho + oy) * Wo + ox) * 64 + ch * 8) = v;
+    }
+  }
+}
+
+int launch_stem7x7s2_fused(const float* x, const void* wpacked, const float* shift, void* y16, int B, int H, int W,
+                           int dtype, cudaStream_t st) {
+  HF_REQUIRE(x && wpacked && shift && y16, "stem7x7s2: null pointer");
+  HF_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "stem7x7s2: bad shape");
+  HF_REQUIRE((((uintptr_t)wpacked | (uintptr_t)y16) & 15) == 0, "stem7x7s2: packed weights / output must be 16-byte aligned");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  dim3 grid(cdiv_s(Wo, kSfCols), cdiv_s(Ho, kSfRows), B);
+  HF_REQUIRE(grid.y <= 65535, "stem7x7s2: image too tall");
+  if (dtype == HF_BF16)
+    stem7x7s2_fused_kernel<HF_BF16><<<grid, 256, 0, st>>>(x, (const uint16_t*)wpacked, shift, (uint16_t*)y16, H, W, Ho, Wo);
+  else
+    stem7x7s2_fused_kernel<HF_F16><<<grid, 256, 0, st>>>(x, (const uint16_t*)wpacked, shift, (uint16_t*)y16, H, W, Ho, Wo);
+  HF_LAUNCH_OK("stem7x7s2_fused");
+  count_launch();
+  return HF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // F.interpolate(x, (H, W), mode='bilinear', align_corners=True) on fp32 NCHW (model.py:239-241): the first C of
 // Cin channel planes of x (the logit convolution pads its 19 classes to 32 output channels).
 // ------------------------------------------------------------------------------------------------

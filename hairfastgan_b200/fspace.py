@@ -75,8 +75,9 @@ def align_f_space(intermediate_align, latent_F_1, latent_F_out_new, latent_F_2, 
     if free_mask.dim() != 4 or free_mask.shape[0] != 3 or free_mask.shape[1] != 1:
         raise RuntimeError(f"align_f_space: free_mask must be [3,1,H,W], got {list(free_mask.shape)}")
     fm = _f32(free_mask)
-    return fspace_blend(intermediate_align, [(latent_F_1, fm[0], 1.0, -1.0), (latent_F_out_new, fm[1], 1.0, -1.0),
-                                             (latent_F_2, fm[2], 1.0, -1.0)])
+    # :157  intermediate_align + low[0] * (latent_F_1 - intermediate_align)  ==  src + w * (F - src) with F = latent_F_1
+    return fspace_blend(latent_F_1, [(intermediate_align, fm[0], 1.0, -1.0), (latent_F_out_new, fm[1], 1.0, -1.0),
+                                     (latent_F_2, fm[2], 1.0, -1.0)])
 
 
 def mix_f_space(latent_F, latent_F_from_W, hair_mask, mixing: float) -> torch.Tensor:

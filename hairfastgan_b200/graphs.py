@@ -11,7 +11,9 @@ replayed: input copied into the graph's static buffer, one `cudaGraphLaunch`, ou
 * keyed on (network, input shape / dtype / device, parameter version key): a weight change recaptures
 * batch <= HAIRFAST_GRAPH_MAX_BATCH (default 8): the graph's private pool holds one set of activations per signature,
   which is only wanted at latency-bound sizes (the throughput path at B = 48 stays eager)
-* no RNG inside these networks; the generator (17 `normal_()` draws per forward, GPU-bound even at B = 1) stays eager
+* the generator forward (`randomize_noise=True`, no explicit noise list) is captured too, its 17 `normal_()` draws
+  included: torch's graph-safe Philox state makes a replay consume exactly the (seed, offset) range the eager call
+  would, so `seed_setter` reproducibility and the reference's draw order hold (tested bit for bit)
 * HAIRFAST_CUDA_GRAPHS=0 disables it; a failed capture disables it for that signature (eager CUDA path, never a CPU one)
 """
 from __future__ import annotations
@@ -60,33 +62,40 @@ class _Entry:
     __slots__ = ("graph", "static_in", "outs", "spec", "pack_key")
 
 
-def _capture(fn, x, pack_key):
+def _capture(fn, xs, pack_key, restore_rng: bool):
     ent = _Entry()
     ent.pack_key = pack_key
-    ent.static_in = x.clone()
-    cur = torch.cuda.current_stream(x.device)
-    side = torch.cuda.Stream(device=x.device)
+    ent.static_in = [None if x is None else x.clone() for x in xs]
+    dev = next(x for x in xs if x is not None).device
+    cur = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(device=dev)
+    rng = torch.cuda.get_rng_state(dev) if restore_rng else None
     side.wait_stream(cur)
     with torch.cuda.stream(side):                       # warm-up on a side stream (PyTorch's capture recipe)
-        fn(ent.static_in)
+        fn(*ent.static_in)
     cur.wait_stream(side)
-    torch.cuda.synchronize(x.device)
+    torch.cuda.synchronize(dev)
+    if rng is not None:                                 # the warm-up's random draws must not count: the replay below is
+        torch.cuda.set_rng_state(rng, dev)              # THE forward of this call and consumes the stream like eager
     ent.graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(ent.graph):
-        out = fn(ent.static_in)
+        out = fn(*ent.static_in)
     ent.outs = []
     ent.spec = _flatten(out, ent.outs)
     return ent
 
 
-def run(owner, tag: str, pack_key, fn, x: torch.Tensor):
-    """`fn(x)` -- eagerly the first time a signature is seen, captured on the second, replayed afterwards."""
-    if (not enabled() or not x.is_cuda or x.dim() < 1 or x.shape[0] > _max_batch()
+def run_multi(owner, tag, pack_key, fn, xs, batch: int, uses_rng: bool = False):
+    """`fn(*xs)` (xs: CUDA tensors or None) -- eagerly the first time a signature is seen, captured on the second call,
+    replayed afterwards.  With `uses_rng` the function draws from torch's CUDA generator inside the graph (graph-safe
+    Philox: a replay consumes the same (seed, offset) range as the eager call would, so seeded runs are unchanged)."""
+    first = next((x for x in xs if x is not None), None)
+    if (not enabled() or first is None or not first.is_cuda or batch > _max_batch()
             or torch.cuda.is_current_stream_capturing()):
         _STATS["eager"] += 1
-        return fn(x)
+        return fn(*xs)
     cache = owner.__dict__.setdefault("_hf_graphs", {})
-    sig = (tag, tuple(x.shape), x.dtype, x.device.index)
+    sig = (tag, tuple(None if x is None else (tuple(x.shape), x.dtype) for x in xs), first.device.index)
     ent = cache.get(sig)
     if isinstance(ent, _Entry) and ent.pack_key != pack_key:
         ent = None                                      # weights changed: drop the stale graph
@@ -94,20 +103,27 @@ def run(owner, tag: str, pack_key, fn, x: torch.Tensor):
     if ent is None:                                     # first sighting: eager (packs weights, sets kernel attributes)
         cache[sig] = 1
         _STATS["eager"] += 1
-        return fn(x)
+        return fn(*xs)
     if ent is False:
         _STATS["eager"] += 1
-        return fn(x)
+        return fn(*xs)
     if ent == 1:
         try:
-            ent = cache[sig] = _capture(fn, x.contiguous(), pack_key)
+            ent = cache[sig] = _capture(fn, [None if x is None else x.contiguous() for x in xs], pack_key, uses_rng)
             _STATS["captures"] += 1
         except Exception:                               # noqa: BLE001 -- not capturable here: stay eager for this signature
             cache[sig] = False
             _STATS["failed"] += 1
-            torch.cuda.synchronize(x.device)
-            return fn(x)
-    ent.static_in.copy_(x)
+            torch.cuda.synchronize(first.device)
+            return fn(*xs)
+    for st, x in zip(ent.static_in, xs):
+        if st is not None:
+            st.copy_(x)
     ent.graph.replay()
     _STATS["replays"] += 1
     return _rebuild(ent.spec, ent.outs)
+
+
+def run(owner, tag: str, pack_key, fn, x: torch.Tensor):
+    """Single-input form (the encoder-family forwards)."""
+    return run_multi(owner, tag, pack_key, fn, (x,), int(x.shape[0]) if x.dim() else 1)

@@ -437,10 +437,18 @@ class Generator(nn.Module):
 
     def _get_workspace(self, cfg, batch, device):
         # one grow-only buffer per device: the layout is recomputed from (cfg, batch) on every call, so a
-        # workspace sized for a larger batch serves every smaller one
+        # workspace sized for a larger batch serves every smaller one.  Captured CUDA graphs bake the pointer in, so a
+        # growth allocates at least the graph batch cap up front and drops the graphs captured on the old buffer.
         nbytes = _lib.lib().hf_generator_workspace_bytes(C.byref(cfg), batch)
         ws = self._workspace.get(str(device))
         if ws is None or ws.numel() < nbytes:
+            from . import graphs
+            if ws is not None:
+                self.__dict__.pop("_hf_graphs", None)             # graphs on the old buffer are dropped with it
+            if graphs.enabled() and batch <= graphs._max_batch():
+                nbytes = max(nbytes, _lib.lib().hf_generator_workspace_bytes(C.byref(cfg), graphs._max_batch()))
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("Generator workspace must be allocated before a CUDA-graph capture")
             ws = self._workspace[str(device)] = _alloc_bytes(nbytes, device)
         return ws
 
@@ -460,7 +468,22 @@ class Generator(nn.Module):
                 input_is_latent=False, noise=None, randomize_noise=True, layer_in=None, skip=None,
                 start_layer=0, end_layer=8, return_rgb=False):
         latent = self._build_latent(styles, inject_index, truncation, truncation_latent, input_is_latent)
-        early, out_feat, out_rgb, _ = self._run(latent, noise, randomize_noise, layer_in, skip, start_layer, end_layer)
+        if noise is None and latent.is_cuda and latent.dim() == 3:
+            # the fixed launch sequence of this (batch, range) signature replays as one CUDA graph (graphs.py); explicit
+            # noise lists / the FSE feature insertion / large batches stay eager
+            from . import graphs
+            cfg = self._ensure_packed(latent.device)
+
+            def fn(lat, lin, sk):
+                early, feat, rgb, _ = self._run(lat, None, randomize_noise, lin, sk, start_layer, end_layer)
+                return early, feat, rgb
+            early, out_feat, out_rgb = graphs.run_multi(
+                self, ("gen", start_layer, end_layer, bool(randomize_noise), cfg.dtype), self._pack_key, fn,
+                (latent if latent.dtype == torch.float32 else latent.float(), layer_in, skip), int(latent.shape[0]),
+                uses_rng=bool(randomize_noise))
+        else:
+            early, out_feat, out_rgb, _ = self._run(latent, noise, randomize_noise, layer_in, skip, start_layer,
+                                                    end_layer)
         if early:
             return out_feat, out_rgb
         return (out_rgb, latent) if return_latents else (out_rgb, None)

@@ -178,17 +178,24 @@ def adaptive_avgpool(x16, oh: int, ow: int, dtype: Optional[int] = None):
 
 # ------------------------------------------------------------------------------------------------ BiSeNet glue
 class PackedStem7x7:
-    """Resnet18.conv1 + bn1 + ReLU (face_parsing/resnet.py:60-61,69-70) = im2col (K = 147, padded to 160) + a 1x1
-    tensor-core convolution with the BatchNorm folded in."""
+    """Resnet18.conv1 + bn1 + ReLU (face_parsing/resnet.py:60-61,69-70) as ONE fused kernel (`hf_stem7x7s2_nhwc16`):
+    the 7x7 window is gathered in shared memory, no im2col tensor in HBM.  Packed weights: 16-bit [64][184] with
+    k = ky*24 + kx*3 + c and the BatchNorm scale folded in; the BatchNorm shift is the epilogue bias."""
 
     def __init__(self, weight: torch.Tensor, bn: torch.nn.BatchNorm2d, dtype: Optional[int] = None):
         self.dtype = default_dtype() if dtype is None else dtype
         scale, self.shift = bn_affine(bn)
-        cout = weight.shape[0]
-        self.conv = PackedConv2d(_f32(weight).reshape(cout, 147, 1, 1), scale, cin_pad=160, dtype=self.dtype)
+        w = _f32(weight)
+        cout = w.shape[0]
+        if tuple(w.shape) != (64, 3, 7, 7):
+            raise NotImplementedError(f"stem7x7s2: expected a [64,3,7,7] weight, got {list(w.shape)}")
+        wk = (w * scale.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(cout, 7, 21)      # [n][ky][kx*3 + c]
+        packed = torch.zeros(cout, 184, device=w.device, dtype=torch.float32)
+        packed[:, :168].view(cout, 7, 24)[:, :, :21] = wk
+        self.wp = packed.to(torch_dtype(self.dtype)).contiguous()
 
     def __call__(self, x: torch.Tensor):
-        """[B,3,H,W] fp32 NCHW -> [B,Ho,Wo,cout] 16-bit NHWC."""
+        """[B,3,H,W] fp32 NCHW -> [B,Ho,Wo,64] 16-bit NHWC."""
         if not x.is_cuda:
             raise RuntimeError("stem7x7s2: input must be a CUDA tensor (no CPU fallback)")
         xf = _f32(x)
@@ -196,11 +203,10 @@ class PackedStem7x7:
         if c != 3:
             raise ValueError("stem7x7s2: expected a 3-channel image")
         ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
-        cols = torch.empty(b, ho, wo, 160, device=x.device, dtype=torch_dtype(self.dtype))
+        y = torch.empty(b, ho, wo, 64, device=x.device, dtype=torch_dtype(self.dtype))
         _lib.use_device(x.device.index)
-        _lib.check(_lib.lib().hf_im2col7x7s2_nhwc16(xf.data_ptr(), cols.data_ptr(), b, h, w, self.dtype, _lib.stream_ptr()),
-                   "hf_im2col7x7s2_nhwc16")
-        y, _, _ = self.conv(cols, shift=self.shift, act=3)
+        _lib.check(_lib.lib().hf_stem7x7s2_nhwc16(xf.data_ptr(), self.wp.data_ptr(), self.shift.data_ptr(), y.data_ptr(),
+                                                  b, h, w, self.dtype, _lib.stream_ptr()), "hf_stem7x7s2_nhwc16")
         return y
 
 

@@ -259,6 +259,12 @@ int hf_adaptive_avgpool_nhwc16(const void* x16, float* y, int batch, int height,
                                int ow, int dtype, void* stream);
 
 /* ---- BiSeNet face parsing (models/CtrlHair/external_code/face_parsing/{model,resnet}.py) ---- */
+/* Resnet18.conv1 7x7/s2/p3 + bn1 + ReLU fused (face_parsing/resnet.py:60-61,69-70): x [B,3,H,W] fp32 NCHW ->
+ * y16 [B,(H+1)/2,(W+1)/2,64] 16-bit NHWC.  wpacked: 16-bit [64][184], row n = weight[n,c,ky,kx] * bn_scale[n] at
+ * k = ky*24 + kx*3 + c (k < 168, kx*3+c < 21), zero elsewhere; shift [64] fp32 = the BatchNorm shift. */
+int hf_stem7x7s2_nhwc16(const float* x, const void* wpacked, const float* shift, void* y16, int batch, int height,
+                        int width, int dtype, void* stream);
+
 /* im2col for Resnet18.conv1 (resnet.py:60,69; 7x7 / stride 2 / pad 3 on 3 channels): x [B,3,H,W] fp32 NCHW ->
  * y16 [B,Ho,Wo,160] 16-bit NHWC, channel k = (c*7 + ky)*7 + kx (= the flattening of the conv weight [64,3,7,7]),
  * zero for k >= 147 and outside the image; Ho = (H-1)/2+1.  The stem is then hf_conv2d_forward with

@@ -212,3 +212,38 @@ def test_consume_noise_advances_rng_like_a_forward():
     assert torch.equal(after_forward, after_skip)
     torch.manual_seed(123)                                              # control: without the draws the stream differs
     assert not torch.equal(after_forward, torch.randn(1000, device="cuda"))
+
+
+def test_generator_cuda_graph_replay_keeps_outputs_and_rng(M, gen256):
+    """graphs.py on the generator: call 1 eager, call 2 captures (17 normal_() draws inside the graph), later calls
+    replay.  Under a fixed seed every call must give the eager image bit for bit AND leave torch's CUDA generator where
+    the eager forward leaves it (the next draw is identical); partial ranges with layer_in likewise."""
+    from hairfastgan_b200 import graphs
+    lat = torch.randn(2, 14, 512, device="cuda")
+    os.environ["HAIRFAST_CUDA_GRAPHS"] = "0"
+    try:
+        torch.manual_seed(3407)
+        want, _ = gen256([lat], input_is_latent=True)
+        after_want = torch.randn(64, device="cuda")
+        lin = torch.randn(2, 512, 16, 16, device="cuda")
+        torch.manual_seed(11)
+        want_part = gen256([lat], input_is_latent=True, start_layer=3, end_layer=4, layer_in=lin)
+    finally:
+        os.environ.pop("HAIRFAST_CUDA_GRAPHS")
+    gen256.__dict__.pop("_hf_graphs", None)
+    s0 = graphs.stats()
+    for _ in range(4):
+        torch.manual_seed(3407)
+        got, _ = gen256([lat], input_is_latent=True)
+        after = torch.randn(64, device="cuda")
+        assert torch.equal(got, want) and torch.equal(after, after_want)
+    for _ in range(3):
+        torch.manual_seed(11)
+        feat, skip = gen256([lat], input_is_latent=True, start_layer=3, end_layer=4, layer_in=lin)
+        assert torch.equal(feat, want_part[0]) and torch.equal(skip, want_part[1])
+    s1 = graphs.stats()
+    assert s1["captures"] >= s0["captures"] + 2 and s1["replays"] >= s0["replays"] + 5 and s1["failed"] == s0["failed"]
+    lat2 = torch.randn(2, 14, 512, device="cuda")                 # same signature, other data
+    torch.manual_seed(3407)
+    other, _ = gen256([lat2], input_is_latent=True)
+    assert not torch.equal(other, want)

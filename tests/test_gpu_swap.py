@@ -24,7 +24,8 @@ pytestmark = [pytest.mark.gpu,
 
 WORK = os.environ.get("HAIRFAST_WORK", "/tmp/hairfast_work")
 # "default" = nothing set in the environment: generator bf16, encoder family fp16 (what a user of install() gets)
-HF_DTYPES = ["default", "fp16"]
+# (HAIRFAST_SWAP_DTYPES=default,fp16,bf16 adds the forced modes: each costs two more 20 s process start-ups)
+HF_DTYPES = os.environ.get("HAIRFAST_SWAP_DTYPES", "default").split(",")
 
 # Stated tolerance of the FINAL 1024^2 image (values in [0,1]) against the stock reference run on the same GPU, same
 # seeds.  The pipeline has discrete decisions (BiSeNet arg-max labels -> 256^2 masks -> F-space blends), so a small set

@@ -17,7 +17,7 @@ if [ "${LEAN_SWAP:-1}" = "1" ]; then
   t0=$(date +%s)
   timeout 900 python baseline/run_swap.py --mode overlay --work /tmp/hairfast_work --reps 5 --warmup 3 > gpurun_out/swap_overlay.json 2> gpurun_out/swap_overlay.err; echo "swap rc=$? ($(( $(date +%s) - t0 )) s)"
   tail -2 gpurun_out/swap_overlay.err; python -c "
-import json; d=json.load(open('gpurun_out/swap_overlay.json'))
+import json; d=json.loads([l for l in open('gpurun_out/swap_overlay.json') if l.startswith('{')][-1])
 for t in d['timings']: print('wall %.1f gpu %.1f hot %.1f'%(t['wall_ms'],t['gpu_ms'],t['hot_path_ms']), {k:round(v,2) for k,v in t['per_module_ms'].items()})
 "
 fi
