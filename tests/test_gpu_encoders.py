@@ -221,7 +221,7 @@ def test_bisenet_golden(N, golden_dir):
     labels = net.parse_labels(x.cuda())
     assert labels.dtype == torch.int64 and labels.shape == (2, 256, 256)
     assert torch.equal(labels, out.argmax(1))
-    x2 = torch.rand(1, 3, 128, 320, generator=torch.Generator().manual_seed(53)).cuda() * 2 - 1
+    x2 = torch.rand(1, 3, 256, 512, generator=torch.Generator().manual_seed(53)).cuda() * 2 - 1
     assert torch.equal(net.parse_labels(x2), net(x2)[0].argmax(1))
 
 
