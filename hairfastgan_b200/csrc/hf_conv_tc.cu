@@ -41,7 +41,6 @@
 namespace hf {
 
 constexpr int kMaxStages = 8;
-constexpr int kMaxG = 8;             // tiles per round (halo kernel)
 constexpr int kTableBytes = 16384;   // 512 entries x 32 B
 constexpr float kSqrt2 = 1.41421356237309515f;
 
@@ -339,115 +338,6 @@ __device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, const T
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Round-level StyledConv epilogue (round 2).  ncu on the low-channel 512^2 / 1024^2 layers
-// (profiles/ncu_hires_layers_r2.json) showed the per-tile epilogue bound by the shared-memory pipe, not by issue
-// slots: every output element paid two LDS.128 of its channel's table entry {d, bias, s_next | w_rgb}, and a
-// warp-wide LDS.128 is 4 wavefronts even when all lanes read one address (512 B of register write-back): 33 M
-// wavefronts = 60 % of the kernel's cycles on 32->32 @1024^2, with the tensor pipe at 18 % of its 27 % ceiling.
-// A thread is tied to ONE pixel (its TMEM lane), so the only reuse axis for a channel's entry is across the tiles that
-// share an accumulator buffer: here 8 channels' entries are loaded ONCE into registers and applied to that
-// 8-channel slice of every tile of the round (and of all four output parities of an up-conv) -- table traffic per
-// element drops by G (x4 for up-convs).  Requires all tiles of the round in the same image (same style row).
-// ---------------------------------------------------------------------------------------------
-template <int DT, bool RGB, bool UP, int GMAX>
-__device__ __noinline__ void epilogue_round_gen(const ConvKernelParams& p, const TableEntry* trow, uint32_t taddr,
-                                                   uint64_t* release_bar, int n0, int nt, int bt, int m0, int gcount,
-                                                   int h_l, int w_l, const float4 nz0, float nw) {
-  constexpr int NPAR = UP ? 4 : 1;
-  const int nc_tile = UP ? p.n_tile / 4 : p.n_tile;                 // channels per tile
-  const size_t plane_o = (size_t)p.Ho * p.Wo;
-  const float slope = p.act ? 0.2f : 1.f, nscale = (p.act ? kSqrt2 : 1.f) * nw;
-  const uint32_t trow_s = smem_u32(trow);
-  uint16_t* const dst_img = p.xhat_out + (size_t)bt * plane_o * p.Cout + (UP ? (n0 >> 2) : n0);
-  float* const rgb_img = RGB ? p.rgb_partial + ((size_t)nt * p.B + bt) * 3 * plane_o : nullptr;
-  // per-tile state in registers (static indices): this thread's pixel inside the image, its noise, its RGB sums
-  int px_off[GMAX];                     // input-resolution pixel index y*W + x  (W = Wo or Wo/2)
-  float nzv[GMAX][NPAR];
-  float rsum[GMAX][3];
-  const int Wi = UP ? p.Wo / 2 : p.Wo;
-#pragma unroll
-  for (int g = 0; g < GMAX; ++g) {
-    rsum[g][0] = rsum[g][1] = rsum[g][2] = 0.f;
-    px_off[g] = 0;
-#pragma unroll
-    for (int par = 0; par < NPAR; ++par) nzv[g][par] = 0.f;
-    if (g < gcount) {
-      const MTile t = decode_mtile(p, m0 + g);
-      const int yi = t.y0 + h_l, xi = t.x0 + w_l;
-      px_off[g] = yi * Wi + xi;
-      const float4 n4 = g == 0 ? nz0 : load_noise(p, bt, yi, xi, nw);
-      nzv[g][0] = nscale * n4.x;
-      if (UP) { nzv[g][1] = nscale * n4.y; nzv[g][2] = nscale * n4.z; nzv[g][3] = nscale * n4.w; }
-    }
-  }
-  const int n_groups = nc_tile / 8;
-#pragma unroll 1
-  for (int cg = 0; cg < n_groups; ++cg) {
-    float ta[8][3], tb[8][3];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 a4 = lds128(trow_s + (uint32_t)(cg * 8 + j) * 32u);
-      ta[j][0] = a4.x; ta[j][1] = a4.y; ta[j][2] = a4.z;
-      if (RGB) {
-        const float4 b4 = lds128(trow_s + (uint32_t)(cg * 8 + j) * 32u + 16u);
-        tb[j][0] = b4.x; tb[j][1] = b4.y; tb[j][2] = b4.z;
-      }
-    }
-    // column of (tile g, parity par) for this channel group inside the accumulator buffer
-    const int col0 = UP ? (cg >> 2) * 128 + (cg & 3) * 8 : cg * 8;
-    uint32_t acc[2][NPAR][8];
-#pragma unroll
-    for (int par = 0; par < NPAR; ++par) tmem_ld_32x32_x8(taddr + (uint32_t)(col0 + par * 32), acc[0][par]);
-#pragma unroll
-    for (int g = 0; g < GMAX; ++g) {
-      if (g < gcount) {
-        tmem_ld_wait();                                  // tile g's slices are in registers
-        if (g + 1 < gcount) {
-#pragma unroll
-          for (int par = 0; par < NPAR; ++par)
-            tmem_ld_32x32_x8(taddr + (uint32_t)((g + 1) * p.n_tile + col0 + par * 32), acc[(g + 1) & 1][par]);
-        } else if (cg == n_groups - 1 && release_bar) {  // that was the last TMEM read of the round
-          tc_fence_before();
-          mbar_arrive(release_bar);
-        }
-        const int yi = px_off[g] / Wi, xi = px_off[g] - yi * Wi;
-#pragma unroll
-        for (int par = 0; par < NPAR; ++par) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int hh = 0; hh < 4; ++hh) {
-            float v[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int j = hh * 2 + u;
-              float a = fmaf(__uint_as_float(acc[g & 1][par][j]), ta[j][0], nzv[g][par] + ta[j][1]);
-              a = fmaxf(a, slope * a);
-              if (RGB) {
-                rsum[g][0] = fmaf(a, tb[j][0], rsum[g][0]);
-                rsum[g][1] = fmaf(a, tb[j][1], rsum[g][1]);
-                rsum[g][2] = fmaf(a, tb[j][2], rsum[g][2]);
-              }
-              v[u] = a * ta[j][2];
-            }
-            pk[hh] = Half2T<DT>::pack(v[0], v[1]);
-          }
-          const size_t opix = UP ? (size_t)(2 * yi + (par >> 1)) * p.Wo + (2 * xi + (par & 1)) : (size_t)px_off[g];
-          *reinterpret_cast<uint4*>(dst_img + opix * p.Cout + cg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        }
-      }
-    }
-  }
-  if (RGB) {
-#pragma unroll
-    for (int g = 0; g < GMAX; ++g)
-      if (g < gcount) {
-        float* pp = rgb_img + px_off[g];
-        pp[0] = rsum[g][0]; pp[plane_o] = rsum[g][1]; pp[2 * plane_o] = rsum[g][2];
-      }
-  }
-}
-
 // =============================================================================================
 // v1: one TMA box per (tap, channel chunk)
 // =============================================================================================
@@ -603,6 +493,7 @@ constexpr int kHaloTW = 8, kHaloTH = 16;
 constexpr int kHaloRows = kHaloTH + 2;
 constexpr int kHaloPitch = kHaloTW + 2;   // dense halo rows (pitch 16 measured no faster)
 constexpr int kMaxASlots = 8;
+constexpr int kMaxG = 8;
 
 // NG = number of epilogue groups (4 warps each) = number of TMEM accumulator buffers of 512/NG columns.  NG = 4
 // (576 threads, <= 112 registers) serves the resident-weight low-channel layers, whose per-tile MMA time is shorter
@@ -808,24 +699,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ++use;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * BUF_COLS);
-      // generator layers writing only the 16-bit operand of the next conv (+ fused ToRGB sums): round-level epilogue
-      // when every tile of the round lies in the same image (one style row -> one table)
-      if (p.epi == 0 && p.xhat_out && !p.out_nchw && !(p.dbg & 1) && p.TB == 1 && (!p.rgb_partial || !p.up) &&
-          gcount <= (p.up ? 2 : (p.rgb_partial ? 4 : 8)) && decode_mtile(p, m0 + gcount - 1).bt == tc.bt) {
-        if (tc.bt != cached_bt || nt != cached_nt) {
-          named_bar_sync(1 + grp, 128);
-          fill_table(p, my_table, etid, tc.bt, n0);
-          named_bar_sync(1 + grp, 128);
-          cached_bt = tc.bt; cached_nt = nt;
-        }
-        if (p.up)
-          epilogue_round_gen<DT, false, true, 2>(p, my_table, taddr, &tmem_empty[grp], n0, nt, tc.bt, m0, gcount, h_l, w_l, nz_next, nw);
-        else if (p.rgb_partial)
-          epilogue_round_gen<DT, true, false, 4>(p, my_table, taddr, &tmem_empty[grp], n0, nt, tc.bt, m0, gcount, h_l, w_l, nz_next, nw);
-        else
-          epilogue_round_gen<DT, false, false, 8>(p, my_table, taddr, &tmem_empty[grp], n0, nt, tc.bt, m0, gcount, h_l, w_l, nz_next, nw);
-        continue;
-      }
       for (int g = 0; g < gcount; ++g) {
         const float4 nz = nz_next;
         const MTile cur = tc;
@@ -1104,14 +977,11 @@ int conv_plan(const ConvLaunch& a, ConvPlan* p) {
     // epilogue-bound with two groups and get four buffers of 128 columns and four groups.  Measured (B=4, us,
     // NG=2 -> NG=4): 32->32@1024^2 220 -> 203, but 64->64@512^2 115 -> 125 and 64->32 up 154 -> 172 (smaller
     // rounds, 96-register budget), so wider layers keep two groups.
-    // (round 2: with the round-level epilogue the table traffic that made those layers epilogue-bound is gone, and two
-    // groups leave 168 registers per thread for its per-tile state: NG = 4 is kept only as a -DHF_DEBUG experiment)
-    p->ng = (p->b_resident && n_tile == 32 && env_int("HF_HALO_NG", 2) == 4) ? 4 : 2;
+    p->ng = (p->b_resident && n_tile == 32 && env_int("HF_HALO_NG", 4) == 4) ? 4 : 2;
     const int buf_cols = 512 / p->ng;
     // rounds: G tiles share one accumulator buffer; keep at least one round per SM
     int G = 1;
-    // the round-level epilogue keeps per-tile ToRGB sums in registers: at most 4 tiles per round on those layers
-    const int gmax = (a.epi == 0 && a.rgb_partial) ? 4 : env_int("HF_HALO_GMAX", kMaxG);
+    const int gmax = env_int("HF_HALO_GMAX", kMaxG);
     while (G * 2 <= gmax && G * 2 * n_tile <= buf_cols &&
            (int64_t)(p->num_m_tiles / (G * 2)) * p->num_n_tiles >= sms)
       G *= 2;
@@ -1281,8 +1151,7 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st, ConvPlan* plan_out) {
     return bf ? launch_pair_kernel(conv_halo2_kernel<HF_BF16>, tmA, tmB, kp, pl, st)
               : launch_pair_kernel(conv_halo2_kernel<HF_F16>, tmA, tmB, kp, pl, st);
   if (pl.halo) {
-#ifdef HF_DEBUG
-    constexpr int T4 = 64 + 128 * 4;          // four epilogue groups: round-1 configuration, kept as an experiment only
+    constexpr int T4 = 64 + 128 * 4;
     if (pl.ng == 4) {
       if (pl.kchunk == 64)
         return bf ? launch_kernel(conv_halo_kernel<64, HF_BF16, 4>, T4, tmA, tmB, kp, pl, st, "conv_halo")
@@ -1290,7 +1159,6 @@ int launch_conv(const ConvLaunch& a, cudaStream_t st, ConvPlan* plan_out) {
       return bf ? launch_kernel(conv_halo_kernel<32, HF_BF16, 4>, T4, tmA, tmB, kp, pl, st, "conv_halo")
                 : launch_kernel(conv_halo_kernel<32, HF_F16, 4>, T4, tmA, tmB, kp, pl, st, "conv_halo");
     }
-#endif
     if (pl.kchunk == 64)
       return bf ? launch_kernel(conv_halo_kernel<64, HF_BF16, 2>, kHaloThreads, tmA, tmB, kp, pl, st, "conv_halo")
                 : launch_kernel(conv_halo_kernel<64, HF_F16, 2>, kHaloThreads, tmA, tmB, kp, pl, st, "conv_halo");
