@@ -24,7 +24,7 @@ import torch
 
 __all__ = ["run", "enabled", "stats"]
 
-_STATS = {"captures": 0, "replays": 0, "eager": 0, "failed": 0}
+_STATS = {"captures": 0, "replays": 0, "eager": 0, "failed": 0, "replayed_kernels": 0}
 
 
 def enabled() -> bool:
@@ -59,7 +59,7 @@ def _rebuild(spec, tensors):
 
 
 class _Entry:
-    __slots__ = ("graph", "static_in", "outs", "spec", "pack_key")
+    __slots__ = ("graph", "static_in", "outs", "spec", "pack_key", "kernels")
 
 
 def _capture(fn, xs, pack_key, restore_rng: bool):
@@ -78,8 +78,11 @@ def _capture(fn, xs, pack_key, restore_rng: bool):
     if rng is not None:                                 # the warm-up's random draws must not count: the replay below is
         torch.cuda.set_rng_state(rng, dev)              # THE forward of this call and consumes the stream like eager
     ent.graph = torch.cuda.CUDAGraph()
+    from . import _lib
+    n0 = _lib.lib().hf_total_launch_count()
     with torch.cuda.graph(ent.graph):
         out = fn(*ent.static_in)
+    ent.kernels = int(_lib.lib().hf_total_launch_count() - n0)    # this library's kernels inside the graph
     ent.outs = []
     ent.spec = _flatten(out, ent.outs)
     return ent
@@ -121,6 +124,7 @@ def run_multi(owner, tag, pack_key, fn, xs, batch: int, uses_rng: bool = False):
             st.copy_(x)
     ent.graph.replay()
     _STATS["replays"] += 1
+    _STATS["replayed_kernels"] += ent.kernels                    # hf_total_launch_count() cannot see a replay
     return _rebuild(ent.spec, ent.outs)
 
 
