@@ -84,9 +84,14 @@ struct ConvKernelParams {
   uint16_t* enc_y16b;
 };
 
+// generator: {d, bias, s_next, w_rgb0 | w_rgb1, w_rgb2, -, -};  encoder: {scale, shift, slope, - | s2, b2, -, -}.
+// A warp-wide shared load costs one wavefront per 128 B of register write-back even when every lane reads the same
+// address (ncu, round 2: the table look-ups were 60 % of the LSU shared pipe on the 1024^2 layer), so each variant
+// fetches exactly the words it uses: LDS.64 + LDS.32 (3 wavefronts) instead of LDS.128 (4) without ToRGB,
+// LDS.128 + LDS.64 (6) instead of 2 x LDS.128 (8) with it.
 struct __align__(16) TableEntry {
-  float d, bias, s_next, pad;
-  float w0, w1, w2, pad2;
+  float d, bias, s_next, w0;
+  float w1, w2, pad, pad2;
 };
 
 struct MTile {
@@ -111,6 +116,7 @@ __device__ __forceinline__ void fill_table(const ConvKernelParams& p, TableEntry
     const int o = (p.up ? (n0 >> 2) : n0) + ol;
     TableEntry t;
     t.d = 1.f; t.bias = 0.f; t.s_next = 1.f; t.pad = 0.f; t.w0 = t.w1 = t.w2 = 0.f; t.pad2 = 0.f;
+    float enc_s2 = 1.f, enc_b2 = 0.f;
     if (p.epi == 1) {            // encoder: {scale, shift, slope, -, s2, b2}
       if (p.enc_scale) t.d = __ldg(p.enc_scale + o);
       if (p.enc_shift) t.bias = __ldg(p.enc_shift + o);
@@ -118,8 +124,9 @@ __device__ __forceinline__ void fill_table(const ConvKernelParams& p, TableEntry
       t.s_next = p.enc_act == 0 ? 1.f
                  : p.enc_act == 3 ? 0.f
                  : (p.enc_act == 1 && p.enc_slope) ? __ldg(p.enc_slope + o) : p.enc_slope0;
-      t.w0 = p.enc_s2 ? __ldg(p.enc_s2 + o) : 1.f;
-      t.w1 = p.enc_b2 ? __ldg(p.enc_b2 + o) : 0.f;
+      enc_s2 = p.enc_s2 ? __ldg(p.enc_s2 + o) : 1.f;
+      enc_b2 = p.enc_b2 ? __ldg(p.enc_b2 + o) : 0.f;
+      t.w1 = enc_s2; t.w2 = enc_b2;                // second half of the entry: {s2, b2}
     } else if (eb < p.B) {
       const size_t bo = (size_t)eb * p.Cout + o;
       if (p.d) t.d = __ldg(p.d + bo);
@@ -155,6 +162,16 @@ __device__ __forceinline__ float4 load_noise(const ConvKernelParams& p, int b, i
   return nz;
 }
 
+__device__ __forceinline__ float2 lds64(uint32_t saddr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
@@ -183,7 +200,9 @@ __device__ __forceinline__ void epi_chunk_enc(uint32_t ts, const uint32_t (&acc)
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int j = g * 8 + h * 2 + u;
-        const float4 ta = lds128(ts + (uint32_t)j * 32u);
+        const float2 t01 = lds64(ts + (uint32_t)j * 32u);             // scale, shift
+        float4 ta;
+        ta.x = t01.x; ta.y = t01.y; ta.z = lds32(ts + (uint32_t)j * 32u + 8u);   // slope
         float a = fmaf(__uint_as_float(acc[j]), ta.x, ta.y);
         if (RES) {
           const float r = Half2T<DT>::to_float((uint16_t)(u ? (rw[h] >> 16) : (rw[h] & 0xFFFFu)));
@@ -200,7 +219,7 @@ __device__ __forceinline__ void epi_chunk_enc(uint32_t ts, const uint32_t (&acc)
         if (NCHW) { if (onchw) onchw[(size_t)j * plane_o] = a; }
         v[u] = a;
         if (Y16B) {
-          const float4 tb = lds128(ts + (uint32_t)j * 32u + 16u);
+          const float2 tb = lds64(ts + (uint32_t)j * 32u + 16u);       // s2, b2
           vb[u] = fmaf(a, tb.x, tb.y);
         }
       }
@@ -266,12 +285,18 @@ __device__ __forceinline__ void epi_chunk(uint32_t ts, const uint32_t (&acc)[32]
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int j = g * 8 + h * 2 + u;
-        const float4 ta = lds128(ts + (uint32_t)j * 32u);            // d, bias, s_next, -
+        float4 ta;                                                   // d, bias, s_next, w_rgb0
+        if (RGB) {
+          ta = lds128(ts + (uint32_t)j * 32u);
+        } else {
+          const float2 t01 = lds64(ts + (uint32_t)j * 32u);
+          ta.x = t01.x; ta.y = t01.y; ta.z = lds32(ts + (uint32_t)j * 32u + 8u); ta.w = 0.f;
+        }
         float a = fmaf(__uint_as_float(acc[j]), ta.x, nzv + ta.y);
         a = fmaxf(a, slope * a);
         if (RGB) {
-          const float4 tb = lds128(ts + (uint32_t)j * 32u + 16u);    // ToRGB weights * style
-          r0 = fmaf(a, tb.x, r0); r1 = fmaf(a, tb.y, r1); r2 = fmaf(a, tb.z, r2);
+          const float2 tb = lds64(ts + (uint32_t)j * 32u + 16u);     // w_rgb1, w_rgb2 (ToRGB weights * style)
+          r0 = fmaf(a, ta.w, r0); r1 = fmaf(a, tb.x, r1); r2 = fmaf(a, tb.y, r2);
         }
         if (NCHW) { if (onchw) onchw[(size_t)j * plane_o] = a; }
         v[u] = a * ta.z;

@@ -177,34 +177,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_up1_k4_strip_kernel(const float
       float v[7];
       const bool row_ok = (r < RS + 3) && iy >= 0 && iy < in_h;
       const float* rp = xp + (size_t)(row_ok ? iy : 0) * in_w + ix0;
-      // rows of the (2R+1)-wide blur input are only 4-byte aligned, and 7 scalar loads per lane (16-byte lane stride)
-      // cost 28 L1 wavefronts per warp row -- the measured limiter (0.65 of the copy peak).  The alignment phase
-      // `al` is the same for every lane of the warp (lanes are 16 bytes apart), so fetch the three ALIGNED float4 that
-      // cover the 7-float window (12 wavefronts) and pick the window with a warp-uniform switch.
-      const int al = (int)((reinterpret_cast<uintptr_t>(rp) >> 2) & 3);
-      if (row_ok && ix0 - al >= 0 && ix0 - al + 12 <= in_w) {
-        const float4* q = reinterpret_cast<const float4*>(rp - al);
-        const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-        const float w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-        switch (al) {
-          case 0:
-#pragma unroll
-            for (int c = 0; c < 7; ++c) v[c] = w[c];
-            break;
-          case 1:
-#pragma unroll
-            for (int c = 0; c < 7; ++c) v[c] = w[c + 1];
-            break;
-          case 2:
-#pragma unroll
-            for (int c = 0; c < 7; ++c) v[c] = w[c + 2];
-            break;
-          default:
-#pragma unroll
-            for (int c = 0; c < 7; ++c) v[c] = w[c + 3];
-            break;
-        }
-      } else if (row_ok && interior) {
+      if (row_ok && interior) {
 #pragma unroll
         for (int c = 0; c < 7; ++c) v[c] = __ldg(rp + c);
       } else {
@@ -259,11 +232,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_up2_k4_strip_kernel(const float
   auto load_row = [&](int iy, float* v) {
     const bool row_ok = iy >= 0 && iy < in_h;
     const float* rp = xp + (size_t)(row_ok ? iy : 0) * in_w + x0 - 1;
-    if (row_ok && interior && ((reinterpret_cast<uintptr_t>(rp + 1) & 15) == 0)) {
-      // columns x0 .. x0+3 are one aligned float4 (x0 % 4 == 0, in_w % 4 == 0); only the two edge columns are scalar
-      const float4 m = __ldg(reinterpret_cast<const float4*>(rp + 1));
-      v[0] = __ldg(rp); v[1] = m.x; v[2] = m.y; v[3] = m.z; v[4] = m.w; v[5] = __ldg(rp + 5);
-    } else if (row_ok && interior) {
+    if (row_ok && interior) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) v[c] = __ldg(rp + c);
     } else {
