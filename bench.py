@@ -389,8 +389,14 @@ def run_ours(args, rank, world, local_rank):
         # BiSeNet at 512^2, B=16
         xs = torch.rand(16, 3, 512, 512, device=dev) * 2 - 1
         ms_seg = avg_ms(lambda: seg(xs))
+        ms_lab = avg_ms(lambda: seg.parse_labels(xs))
         extra["bisenet_b16_512"] = {"img_per_s": round(16e3 / ms_seg, 1),
-                                    "tflops_algorithmic": round(16 * GFLOP_SEG_512 / ms_seg, 1)}
+                                    "tflops_algorithmic": round(16 * GFLOP_SEG_512 / ms_seg, 1),
+                                    "labels_only_img_per_s": round(16e3 / ms_lab, 1),
+                                    "labels_only_tflops_algorithmic": round(16 * GFLOP_SEG_512 / ms_lab, 1),
+                                    "note": "forward = three fp32 logit maps; labels_only = BiSeNet.parse_labels, the "
+                                            "path face parsing takes under install() (same labels; FLOPs counted in "
+                                            "the reference's three-head formulation)"}
         del xs
         # SURVEY 8d metric (3): the standalone HBM-bound operators (module-level API a6 / a7), GB/s = (in + out) / time
         import hairfastgan_b200.op as OP
@@ -671,7 +677,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--triples", type=int, default=16, help="independent triples batched per step and GPU")
+    ap.add_argument("--triples", type=int, default=32, help="independent triples batched per step and GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-network / per-operator side measurements")
     ap.add_argument("--profile-step", action="store_true", help="run one step between cudaProfilerStart/Stop, no JSON")
