@@ -146,54 +146,126 @@ __global__ void __launch_bounds__(256) upfirdn2d_up2_k4_kernel(const float* __re
 // row); the 4x4 FIR costs 64 FMAs per float4 of output, well under the issue budget of an HBM-bound kernel.
 // ---------------------------------------------------------------------------------------------
 // up = 1, down = 1, 4x4 taps, any pad >= 0 (the Blur after the transposed convolution, model.py:77-93).
+// Input side (round 2, after ncu: the register-window loads left every warp with ~1 row in flight -- long-scoreboard
+// stalls 15 per issue, 0.65 of the copy peak): each warp owns a ring of kUpStages row segments in shared memory and
+// keeps kUpStages - 1 rows AHEAD in flight with 4-byte cp.async (the (2R+1)-wide rows are only 4-byte aligned, so
+// neither 16-byte cp.async nor TMA applies): lane l copies elements l, l+32, ... of the 131-float segment, fully
+// coalesced, zero-filled outside the image (= the padding).  No block-level synchronisation: a warp only waits for
+// its own copy groups.
+constexpr int kUpStages = 8;                                 // power of two: slot = row & 7
+constexpr int kUpSeg = 136;                                  // 128 + 3 taps, padded to a multiple of 8 floats
+
+__device__ __forceinline__ void cp_async4_zfill(uint32_t dst_s, const float* src, bool pred) {
+  const int sz = pred ? 4 : 0;                               // src-size 0: the 4 destination bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_s), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int RS>
 __global__ void __launch_bounds__(256) upfirdn2d_up1_k4_strip_kernel(const float* __restrict__ x,
                                                                      float* __restrict__ y,
                                                                      const float* __restrict__ k, int in_h, int in_w,
-                                                                     int out_h, int out_w, int px0, int py0) {
+                                                                     int out_h, int out_w, int px0, int py0, int wx) {
+  // wx (1, 2, 4 or 8) warps of a CTA sit SIDE BY SIDE (wx x 128 columns, up to a whole 1024-wide row) and walk down the
+  // same RS rows; the other 8 / wx warp groups take the strips below
+  __shared__ __align__(16) float ring[8][kUpStages][kUpSeg];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ox = blockIdx.x * 128 + lane * 4;
-  const int oy0 = (blockIdx.y * 8 + warp) * RS;
-  if (oy0 >= out_h) return;
+  const int oxw = (blockIdx.x * wx + (warp & (wx - 1))) * 128;       // first output column of this warp
+  const int ox = oxw + lane * 4;
+  const int oy0 = (blockIdx.y * (8 / wx) + warp / wx) * RS;
+  if (oy0 >= out_h || oxw >= out_w) return;                           // whole warps only: the ring is per warp
   float kr[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) kr[i] = __ldg(k + 15 - i);           // flipped taps: kr[a*4+b] = k[3-a][3-b]
+  // rank-1 test on the flipped taps: kr[a][b] == ky[a] * kx[b] with kx = row 0, ky = column 0 / kr[0][0]
+  float kx[4], ky[4];
+  bool separable = kr[0] != 0.f;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) kx[b] = kr[b];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) ky[a] = separable ? kr[a * 4] / kr[0] : 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      separable = separable && fabsf(ky[a] * kx[b] - kr[a * 4 + b]) <= 1e-6f * fabsf(kr[a * 4 + b]) + 1e-30f;
   const float* xp = x + (size_t)blockIdx.z * in_h * in_w;
   float* yp = y + (size_t)blockIdx.z * out_h * out_w;
-  const int ix0 = ox - px0;
-  const bool interior = ix0 >= 0 && ix0 + 6 < in_w;
+  const int ixw = oxw - px0;                                          // first input column of the warp's segment
   const bool vec_store = ((out_w & 3) == 0) && ox + 3 < out_w;
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(&ring[warp][0][0]);
+  constexpr int NROWS = RS + 3;
+  // row r of the strip (input row iy = oy0 - py0 + r) -> ring slot r & (kUpStages - 1).  The column part of every
+  // copy (offset, in-bounds flag, shared address) is row-invariant and computed once
+  int gxo[5];
+  uint32_t dsto[5];
+  bool okx[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const int e = j * 32 + lane, gx = ixw + e;
+    okx[j] = e < 131 && gx >= 0 && gx < in_w;
+    gxo[j] = okx[j] ? gx : 0;
+    dsto[j] = ring_s + (uint32_t)(e < 131 ? e : 0) * 4u;
+  }
+  auto issue_row = [&](int r) {
+    const int iy = oy0 - py0 + r;
+    const bool row_ok = r < NROWS && iy >= 0 && iy < in_h;
+    const float* rp = xp + (size_t)(row_ok ? iy : 0) * in_w;
+    const uint32_t slot_off = (uint32_t)((r & (kUpStages - 1)) * kUpSeg) * 4u;
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+      if (j < 4 || lane < 3)                                          // element 128 + lane exists for lanes 0..2 only
+        cp_async4_zfill(dsto[j] + slot_off, rp + gxo[j], row_ok && okx[j]);
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int r = 0; r < kUpStages - 1; ++r) issue_row(r);
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 #pragma unroll 1
-  for (int r0 = 0; r0 < RS + 3; r0 += 4) {
+  for (int r0 = 0; r0 < NROWS; r0 += 4) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int r = r0 + u;
-      const int iy = oy0 - py0 + r;
-      float v[7];
-      const bool row_ok = (r < RS + 3) && iy >= 0 && iy < in_h;
-      const float* rp = xp + (size_t)(row_ok ? iy : 0) * in_w + ix0;
-      if (row_ok && interior) {
+      issue_row(r + kUpStages - 1);                                   // always commits a (possibly empty) group
+      cp_async_wait<kUpStages - 1>();                                 // row r has landed (this lane's copies) ...
+      __syncwarp();                                                   // ... and every other lane's
+      const float* seg = &ring[warp][r & (kUpStages - 1)][lane * 4];
+      const float4 s0 = *reinterpret_cast<const float4*>(seg);
+      const float4 s1 = *reinterpret_cast<const float4*>(seg + 4);
+      const float v[7] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z};
+      __syncwarp();                                                   // slot may be refilled by the next issue_row
+      // input row r feeds output rows r - a (a = tap row); (r - a) & 3 == (u - a) & 3 because r0 % 4 == 0
+      if (separable) {
+        // rank-1 FIR (every make_kernel() blur: outer(k1, k1)): one horizontal pass per input row, then 4 scaled adds
+        float hrow[4];
 #pragma unroll
-        for (int c = 0; c < 7; ++c) v[c] = __ldg(rp + c);
+        for (int j = 0; j < 4; ++j) {
+          float t = v[j] * kx[0];
+#pragma unroll
+          for (int b = 1; b < 4; ++b) t = fmaf(v[j + b], kx[b], t);
+          hrow[j] = t;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[(u - a) & 3][j] = fmaf(hrow[j], ky[a], acc[(u - a) & 3][j]);
       } else {
 #pragma unroll
-        for (int c = 0; c < 7; ++c) v[c] = (row_ok && ix0 + c >= 0 && ix0 + c < in_w) ? __ldg(rp + c) : 0.f;
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[(u - a) & 3][j] = fmaf(v[j + b], kr[a * 4 + b], acc[(u - a) & 3][j]);
       }
-      // input row r feeds output rows r - a (a = tap row); (r - a) & 3 == (u - a) & 3 because r0 % 4 == 0
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) acc[(u - a) & 3][j] = fmaf(v[j + b], kr[a * 4 + b], acc[(u - a) & 3][j]);
       const int orow = r - 3;                                        // complete once its a = 3 row has arrived
       const int slot = (u + 1) & 3;
-      if (orow >= 0 && orow < RS && oy0 + orow < out_h) {
+      if (orow >= 0 && orow < RS && oy0 + orow < out_h && ox < out_w) {
         float* dst = yp + (size_t)(oy0 + orow) * out_w + ox;
         if (vec_store) {
           __stcs(reinterpret_cast<float4*>(dst), make_float4(acc[slot][0], acc[slot][1], acc[slot][2], acc[slot][3]));
@@ -207,6 +279,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_up1_k4_strip_kernel(const float
       for (int j = 0; j < 4; ++j) acc[slot][j] = 0.f;
     }
   }
+  cp_async_wait<0>();
 }
 
 // up = 2, down = 1, 4x4 taps, pad (2,1): the RGB-skip Upsample (model.py:35-53), out = 2 x in.  Output parity (py,px)
@@ -215,10 +288,11 @@ __global__ void __launch_bounds__(256) upfirdn2d_up1_k4_strip_kernel(const float
 template <int RS>
 __global__ void __launch_bounds__(256) upfirdn2d_up2_k4_strip_kernel(const float* __restrict__ x,
                                                                      float* __restrict__ y,
-                                                                     const float* __restrict__ k, int in_h, int in_w) {
+                                                                     const float* __restrict__ k, int in_h, int in_w,
+                                                                     int wx) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int x0 = blockIdx.x * 128 + lane * 4;
-  const int y0 = (blockIdx.y * 8 + warp) * RS;
+  const int x0 = (blockIdx.x * wx + (warp & (wx - 1))) * 128 + lane * 4;   // wx warps side by side (see the up1 kernel)
+  const int y0 = (blockIdx.y * (8 / wx) + warp / wx) * RS;
   if (y0 >= in_h || x0 >= in_w) return;
   float kr[16];
 #pragma unroll
@@ -326,14 +400,16 @@ int launch_upfirdn2d(const float* x, float* y, const float* k, int planes, int i
   const bool k4 = (kh == 4 && kw == 4);
   const bool sym = (up_x == up_y && down_x == down_y);
   if (k4 && sym && up_x == 1 && down_x == 1 && planes <= 65535 && px0 >= 0 && py0 >= 0 && px1 >= 0 && py1 >= 0) {
-    constexpr int RS = 16;                                   // 8 warps x 16 rows x 128 columns per CTA
-    dim3 grid(cdiv(out_w, 128), cdiv(out_h, 8 * RS), planes);
-    upfirdn2d_up1_k4_strip_kernel<RS><<<grid, 256, 0, st>>>(x, y, k, in_h, in_w, out_h, out_w, px0, py0);
+    constexpr int RS = 64;                                   // rows per warp strip (3 halo rows each)
+    const int wx = out_w > 512 ? 8 : out_w > 256 ? 4 : out_w > 128 ? 2 : 1;   // warps side by side
+    dim3 grid(cdiv(out_w, 128 * wx), cdiv(out_h, RS * (8 / wx)), planes);
+    upfirdn2d_up1_k4_strip_kernel<RS><<<grid, 256, 0, st>>>(x, y, k, in_h, in_w, out_h, out_w, px0, py0, wx);
   } else if (k4 && sym && up_x == 2 && down_x == 1 && planes <= 65535 && px0 == 2 && py0 == 2 && px1 == 1 &&
              py1 == 1) {
-    constexpr int RS = 12;                                   // 8 warps x 12 input rows x 128 input columns per CTA
-    dim3 grid(cdiv(in_w, 128), cdiv(in_h, 8 * RS), planes);
-    upfirdn2d_up2_k4_strip_kernel<RS><<<grid, 256, 0, st>>>(x, y, k, in_h, in_w);
+    constexpr int RS = 12;                                   // input rows per warp strip
+    const int wx = 1;              // warps stacked vertically (measured: 4.9 TB/s vs 4.5 side by side for 512-wide planes)
+    dim3 grid(cdiv(in_w, 128 * wx), cdiv(in_h, RS * (8 / wx)), planes);
+    upfirdn2d_up2_k4_strip_kernel<RS><<<grid, 256, 0, st>>>(x, y, k, in_h, in_w, wx);
   } else if (k4 && sym && up_x == 1 && (down_x == 1 || down_x == 2) && planes <= 65535) {
     if (down_x == 1) {
       dim3 grid(cdiv(out_w, 64), cdiv(out_h, 32), planes);
