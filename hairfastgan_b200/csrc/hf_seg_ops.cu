@@ -286,86 +286,106 @@ template <int DT>
 __global__ void __launch_bounds__(256, 2) stem7x7s2_fused_kernel(const float* __restrict__ x,
                                                                  const uint16_t* __restrict__ wp,
                                                                  const float* __restrict__ shift,
-                                                                 uint16_t* __restrict__ y, int H, int W, int Ho, int Wo) {
-  // [input window | weights]; after the MMA loop the same bytes are the swizzled 256 x 64 output staging tile
-  __shared__ __align__(16) uint16_t sm[kSfInRows * kSfInPitch + 64 * kSfWPitch];
-  uint16_t* in_s = sm;
-  uint16_t* w_s = sm + kSfInRows * kSfInPitch;
-  const int b = blockIdx.z, oy0 = blockIdx.y * kSfRows, ox0 = blockIdx.x * kSfCols;
+                                                                 uint16_t* __restrict__ y, int H, int W, int Ho, int Wo,
+                                                                 int tiles_x, int tiles_y, int total_tiles) {
+  // persistent CTA: the 23 KB of packed weights are loaded ONCE and stay in shared memory while the CTA walks over its
+  // tiles (first version: one tile per CTA re-read them 12 k times per launch and ran at 82 TFLOP/s)
+  extern __shared__ __align__(16) uint8_t stem_smem[];
+  uint16_t* w_s = reinterpret_cast<uint16_t*>(stem_smem);                       // [64][184]
+  uint16_t* in_s = w_s + 64 * kSfWPitch;                                          // [22][216]
+  uint16_t* out_s = in_s + kSfInRows * kSfInPitch;                                // [256][64], chunk ^ (pixel & 7)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* xb = x + (size_t)b * 3 * H * W;
-  // ---- stage the 22 x 72 x 3 input window (zero outside the image = the conv padding), interleaved [row][x*3 + c]
-  const int gy0 = 2 * oy0 - 3, gx0 = 2 * ox0 - 3;
-  for (int i = threadIdx.x; i < 3 * kSfInRows * 72; i += 256) {
-    const int cx = i % 72, t = i / 72, r = t % kSfInRows, c = t / kSfInRows;
-    const int gy = gy0 + r, gx = gx0 + cx;
-    const float v = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(xb + ((size_t)c * H + gy) * W + gx) : 0.f;
-    in_s[r * kSfInPitch + cx * 3 + c] = Half2T<DT>::one(v);
-  }
   for (int i = threadIdx.x; i < 64 * kSfWPitch / 8; i += 256)
     reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(wp) + i);
-  __syncthreads();
-
-  float acc[2][8][4];
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
   const int g4 = lane >> 2, q2 = (lane & 3) * 2;
-  // A[pixel (warp, ox)][k = ky*24 + t] = in_s[2*warp + ky][6*ox + t]
-  const uint16_t* a_row = in_s + (2 * warp) * kSfInPitch;
+  float sh[8][2];
 #pragma unroll
-  for (int ks = 0; ks < kSfK / 16; ++ks) {
-    int off[2];
+  for (int j = 0; j < 8; ++j) { sh[j][0] = __ldg(shift + j * 8 + q2); sh[j][1] = __ldg(shift + j * 8 + q2 + 1); }
+  const int fr = threadIdx.x >> 6, fc = threadIdx.x & 63;                        // fill: 4 rows x 64 columns per pass
+
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x, t2 = tile / tiles_x, ty = t2 % tiles_y, b = t2 / tiles_y;
+    const int oy0 = ty * kSfRows, ox0 = tx * kSfCols;
+    const float* xb = x + (size_t)b * 3 * H * W;
+    // ---- stage the 22 x 72 x 3 input window (zero outside the image = the conv padding), interleaved [row][x*3 + c]
+    const int gy0 = 2 * oy0 - 3, gx0 = 2 * ox0 - 3;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int kk = ks * 16 + 8 * j + q2;
-      off[j] = (kk / 24) * kSfInPitch + (kk % 24);
-    }
-    uint32_t a[2][4];
+    for (int c = 0; c < 3; ++c) {
+      const float* xc = xb + (size_t)c * H * W;
+      for (int r = fr; r < kSfInRows; r += 4) {
+        const int gy = gy0 + r;
+        const bool row_ok = gy >= 0 && gy < H;
+        const float* xr = xc + (size_t)(row_ok ? gy : 0) * W;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int oxa = i * 16 + g4;
-      a[i][0] = *reinterpret_cast<const uint32_t*>(a_row + 6 * oxa + off[0]);
-      a[i][1] = *reinterpret_cast<const uint32_t*>(a_row + 6 * (oxa + 8) + off[0]);
-      a[i][2] = *reinterpret_cast<const uint32_t*>(a_row + 6 * oxa + off[1]);
-      a[i][3] = *reinterpret_cast<const uint32_t*>(a_row + 6 * (oxa + 8) + off[1]);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      uint32_t bf[2];
-      const uint16_t* wrow = w_s + (j * 8 + g4) * kSfWPitch + ks * 16 + q2;
-      bf[0] = *reinterpret_cast<const uint32_t*>(wrow);
-      bf[1] = *reinterpret_cast<const uint32_t*>(wrow + 8);
-      mma16816<DT>(acc[0][j], a[0], bf);
-      mma16816<DT>(acc[1][j], a[1], bf);
-    }
-  }
-  __syncthreads();                                       // everyone is done with in_s / w_s: reuse as output staging
-  // ---- epilogue: + shift (BatchNorm folded: scale lives in the weights), ReLU, 16-bit, swizzled staging
-  uint16_t* out_s = sm;                                  // [256 pixels][64 ch], 16-byte chunk index ^ (pixel & 7)
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float s0 = __ldg(shift + j * 8 + q2), s1 = __ldg(shift + j * 8 + q2 + 1);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int pix = warp * 32 + i * 16 + g4 + 8 * h;
-        const float v0 = fmaxf(acc[i][j][2 * h] + s0, 0.f), v1 = fmaxf(acc[i][j][2 * h + 1] + s1, 0.f);
-        *reinterpret_cast<uint32_t*>(out_s + pix * 64 + ((j ^ (pix & 7)) * 8) + q2) = Half2T<DT>::pack(v0, v1);
+        for (int cx = fc; cx < 72; cx += 64) {
+          const int gx = gx0 + cx;
+          const float v = (row_ok && gx >= 0 && gx < W) ? __ldg(xr + gx) : 0.f;
+          in_s[r * kSfInPitch + cx * 3 + c] = Half2T<DT>::one(v);
+        }
       }
     }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 256 * 8; i += 256) {
-    const int pix = i >> 3, ch = i & 7;
-    const int oy = oy0 + (pix >> 5), ox = ox0 + (pix & 31);
-    if (oy < Ho && ox < Wo) {
-      const uint4 v = *reinterpret_cast<const uint4*>(out_s + pix * 64 + ((ch ^ (pix & 7)) * 8));
-      *reinterpret_cast<uint4*>(y + (((size_t)b * Ho + oy) * Wo + ox) * 64 + ch * 8) = v;
+    __syncthreads();
+
+    float acc[2][8][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+    // A[pixel (warp, ox)][k = ky*24 + t] = in_s[2*warp + ky][6*ox + t]
+    const uint16_t* a_row = in_s + (2 * warp) * kSfInPitch;
+#pragma unroll
+    for (int ks = 0; ks < kSfK / 16; ++ks) {
+      int off[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int kk = ks * 16 + 8 * j + q2;
+        off[j] = (kk / 24) * kSfInPitch + (kk % 24);
+      }
+      uint32_t a[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int oxa = i * 16 + g4;
+        a[i][0] = *reinterpret_cast<const uint32_t*>(a_row + 6 * oxa + off[0]);
+        a[i][1] = *reinterpret_cast<const uint32_t*>(a_row + 6 * (oxa + 8) + off[0]);
+        a[i][2] = *reinterpret_cast<const uint32_t*>(a_row + 6 * oxa + off[1]);
+        a[i][3] = *reinterpret_cast<const uint32_t*>(a_row + 6 * (oxa + 8) + off[1]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t bf[2];
+        const uint16_t* wrow = w_s + (j * 8 + g4) * kSfWPitch + ks * 16 + q2;
+        bf[0] = *reinterpret_cast<const uint32_t*>(wrow);
+        bf[1] = *reinterpret_cast<const uint32_t*>(wrow + 8);
+        mma16816<DT>(acc[0][j], a[0], bf);
+        mma16816<DT>(acc[1][j], a[1], bf);
+      }
     }
+    // ---- epilogue: + shift (BatchNorm folded: scale lives in the weights), ReLU, 16-bit, swizzled staging (its own
+    // buffer: the previous tile's copy-out finished before this tile's fill barrier)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int pix = warp * 32 + i * 16 + g4 + 8 * h;
+          const float v0 = fmaxf(acc[i][j][2 * h] + sh[j][0], 0.f), v1 = fmaxf(acc[i][j][2 * h + 1] + sh[j][1], 0.f);
+          *reinterpret_cast<uint32_t*>(out_s + pix * 64 + ((j ^ (pix & 7)) * 8) + q2) = Half2T<DT>::pack(v0, v1);
+        }
+      }
+    __syncthreads();                                     // staging complete; also: everyone is done reading in_s
+    for (int i = threadIdx.x; i < 256 * 8; i += 256) {
+      const int pix = i >> 3, ch = i & 7;
+      const int oy = oy0 + (pix >> 5), ox = ox0 + (pix & 31);
+      if (oy < Ho && ox < Wo) {
+        const uint4 v = *reinterpret_cast<const uint4*>(out_s + pix * 64 + ((ch ^ (pix & 7)) * 8));
+        *reinterpret_cast<uint4*>(y + (((size_t)b * Ho + oy) * Wo + ox) * 64 + ch * 8) = v;
+      }
+    }
+    // the next iteration's fill writes in_s (free since the barrier above) and its first barrier orders the out_s
+    // reads above against the next epilogue's writes
   }
 }
 
@@ -375,12 +395,20 @@ int launch_stem7x7s2_fused(const float* x, const void* wpacked, const float* shi
   HF_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "stem7x7s2: bad shape");
   HF_REQUIRE((((uintptr_t)wpacked | (uintptr_t)y16) & 15) == 0, "stem7x7s2: packed weights / output must be 16-byte aligned");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  dim3 grid(cdiv_s(Wo, kSfCols), cdiv_s(Ho, kSfRows), B);
-  HF_REQUIRE(grid.y <= 65535, "stem7x7s2: image too tall");
-  if (dtype == HF_BF16)
-    stem7x7s2_fused_kernel<HF_BF16><<<grid, 256, 0, st>>>(x, (const uint16_t*)wpacked, shift, (uint16_t*)y16, H, W, Ho, Wo);
-  else
-    stem7x7s2_fused_kernel<HF_F16><<<grid, 256, 0, st>>>(x, (const uint16_t*)wpacked, shift, (uint16_t*)y16, H, W, Ho, Wo);
+  const int tiles_x = cdiv_s(Wo, kSfCols), tiles_y = cdiv_s(Ho, kSfRows);
+  const int64_t total = (int64_t)tiles_x * tiles_y * B;
+  HF_REQUIRE(total < (int64_t)2000000000, "stem7x7s2: too many tiles");
+  const size_t smem = (size_t)(64 * kSfWPitch + kSfInRows * kSfInPitch + 256 * 64) * sizeof(uint16_t);   // 65.8 KB
+  const int grid = (int)std::min<int64_t>(total, (int64_t)num_sms() * 2);
+  if (dtype == HF_BF16) {
+    HF_CUDA_OK(cudaFuncSetAttribute(stem7x7s2_fused_kernel<HF_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stem7x7s2_fused_kernel<HF_BF16><<<grid, 256, smem, st>>>(x, (const uint16_t*)wpacked, shift, (uint16_t*)y16, H, W, Ho,
+                                                             Wo, tiles_x, tiles_y, (int)total);
+  } else {
+    HF_CUDA_OK(cudaFuncSetAttribute(stem7x7s2_fused_kernel<HF_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stem7x7s2_fused_kernel<HF_F16><<<grid, 256, smem, st>>>(x, (const uint16_t*)wpacked, shift, (uint16_t*)y16, H, W, Ho,
+                                                            Wo, tiles_x, tiles_y, (int)total);
+  }
   HF_LAUNCH_OK("stem7x7s2_fused");
   count_launch();
   return HF_OK;
