@@ -112,8 +112,35 @@ def main():
         return res
     hair_fast.embed.embedding_images = embedding_images
 
+    # optional stage trace (HF_SWAP_TRACE=1): wall time of every stage call, gc collections and graph statistics per rep
+    trace = os.environ.get("HF_SWAP_TRACE") in ("1", "2")           # 2: wall clock only, no synchronize
+    trace_sync = os.environ.get("HF_SWAP_TRACE") == "1"
+    stage_ms = {}
+    if trace:
+        import gc
+
+        def wrap(obj, name, label):
+            orig = getattr(obj, name)
+
+            def timed(*args, **kwargs):
+                if trace_sync:
+                    torch.cuda.synchronize()
+                t0 = time.time()
+                out = orig(*args, **kwargs)
+                if trace_sync:
+                    torch.cuda.synchronize()
+                stage_ms[label] = stage_ms.get(label, 0.0) + (time.time() - t0) * 1e3
+                return out
+            setattr(obj, name, timed)
+        wrap(hair_fast.embed, "embedding_images", "embed")
+        wrap(hair_fast.align, "align_images", "align")
+        wrap(hair_fast.align, "shape_module", "shape_module(incl. in align)")
+        wrap(hair_fast.blend, "blend_images", "blend")
     finals, timings = [], []
     for rep in range(a.warmup + a.reps):
+        if trace:
+            stage_ms.clear()
+            gc0 = [g["collections"] for g in gc.get_stats()]
         spans.clear()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -127,6 +154,15 @@ def main():
         for name, s, e in spans:
             per[name] = per.get(name, 0.0) + s.elapsed_time(e)
         hot_ms = sum(per.values())
+        if trace:
+            line = {"rep": rep, "wall_ms": round(wall, 1), "gpu_ms": round(e0.elapsed_time(e1), 1), "stages": {k: round(v, 1) for k, v in stage_ms.items()},
+                    "gc": [g["collections"] - c for g, c in zip(gc.get_stats(), gc0)]}
+            try:
+                from hairfastgan_b200 import graphs as _g
+                line["graphs"] = _g.stats()
+            except Exception:   # noqa: BLE001
+                pass
+            print("TRACE " + json.dumps(line), file=sys.stderr, flush=True)
         if rep >= a.warmup:
             finals.append(final.detach().float().cpu())
             timings.append({"wall_ms": wall, "gpu_ms": e0.elapsed_time(e1), "hot_path_ms": hot_ms,
@@ -141,7 +177,10 @@ def main():
                          "generator %s, encoders %s" % (os.environ.get("HAIRFAST_DTYPE", "bf16"),
                                                         os.environ.get("HAIRFAST_ENC_DTYPE") or
                                                         os.environ.get("HAIRFAST_DTYPE", "fp16"))),
-               "generator_class": type(hair_fast.net.generator).__module__}
+               "generator_class": type(hair_fast.net.generator).__module__,
+               "cuda_alloc_retries": int(torch.cuda.memory_stats().get("num_alloc_retries", 0)),
+               "cuda_reserved_gb": round(torch.cuda.memory_reserved() / 2 ** 30, 2),
+               "cuda_peak_allocated_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}
     print(json.dumps(summary))
     if a.out:
         torch.save({"finals": finals, "embed": dict(captured), "summary": summary}, a.out)
