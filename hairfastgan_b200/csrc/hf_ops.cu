@@ -282,6 +282,129 @@ __global__ void __launch_bounds__(256) upfirdn2d_up1_k4_strip_kernel(const float
   cp_async_wait<0>();
 }
 
+// up = 1, down = 2, 4x4 taps, pad >= 0 (the Downsample / ConvLayer blur of the reference, model.py:56-74; not on the
+// swap path): same scheme as the up1 kernel -- per-warp cp.async ring, register accumulators -- with two input rows
+// and 2 x 128 + 2 input columns per output row.  Input row r = 2m + e feeds output row m with tap row e and output
+// row m - 1 with tap row e + 2, so two accumulator rows are live.
+constexpr int kDnStages = 4;
+constexpr int kDnSeg = 264;                                  // 258 floats per row segment, padded
+
+template <int RS>
+__global__ void __launch_bounds__(256) upfirdn2d_down2_k4_strip_kernel(const float* __restrict__ x,
+                                                                       float* __restrict__ y,
+                                                                       const float* __restrict__ k, int in_h, int in_w,
+                                                                       int out_h, int out_w, int px0, int py0) {
+  __shared__ __align__(16) float ring[8][kDnStages][kDnSeg];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int oxw = blockIdx.x * 128;
+  const int ox = oxw + lane * 4;
+  const int oy0 = (blockIdx.y * 8 + warp) * RS;
+  if (oy0 >= out_h) return;                                           // whole warps only: the ring is per warp
+  float kr[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kr[i] = __ldg(k + 15 - i);           // flipped taps: kr[a*4+b] = k[3-a][3-b]
+  float kx[4], ky[4];
+  bool separable = kr[0] != 0.f;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) kx[b] = kr[b];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) ky[a] = separable ? kr[a * 4] / kr[0] : 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      separable = separable && fabsf(ky[a] * kx[b] - kr[a * 4 + b]) <= 1e-6f * fabsf(kr[a * 4 + b]) + 1e-30f;
+  const float* xp = x + (size_t)blockIdx.z * in_h * in_w;
+  float* yp = y + (size_t)blockIdx.z * out_h * out_w;
+  const int ixw = 2 * oxw - px0;                                      // first input column of the warp's segment
+  const int iy_first = 2 * oy0 - py0;                                 // input row of strip row 0
+  const bool vec_store = ((out_w & 3) == 0) && ox + 3 < out_w;
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(&ring[warp][0][0]);
+  constexpr int NROWS = 2 * RS + 2;
+  int gxo[9];
+  bool okx[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    const int e = j * 32 + lane, gx = ixw + e;
+    okx[j] = e < 258 && gx >= 0 && gx < in_w;
+    gxo[j] = okx[j] ? gx : 0;
+  }
+  auto issue_row = [&](int r) {
+    const int iy = iy_first + r;
+    const bool row_ok = r < NROWS && iy >= 0 && iy < in_h;
+    const float* rp = xp + (size_t)(row_ok ? iy : 0) * in_w;
+    const uint32_t dst = ring_s + (uint32_t)((r & (kDnStages - 1)) * kDnSeg + lane) * 4u;
+#pragma unroll
+    for (int j = 0; j < 9; ++j)
+      if (j < 8 || lane < 2)                                          // elements 256, 257 exist for lanes 0, 1 only
+        cp_async4_zfill(dst + (uint32_t)(j * 32) * 4u, rp + gxo[j], row_ok && okx[j]);
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int r = 0; r < kDnStages - 1; ++r) issue_row(r);
+  float acc[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
+  for (int r0 = 0; r0 < NROWS; r0 += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u;                                           // r = 2m + e with m = r0/2 + (u >> 1), e = u & 1
+      issue_row(r + kDnStages - 1);
+      cp_async_wait<kDnStages - 1>();
+      __syncwarp();
+      const float* seg = &ring[warp][r & (kDnStages - 1)][lane * 8];
+      const float4 s0 = *reinterpret_cast<const float4*>(seg);
+      const float4 s1 = *reinterpret_cast<const float4*>(seg + 4);
+      const float4 s2 = *reinterpret_cast<const float4*>(seg + 8);
+      const float v[10] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y};
+      __syncwarp();
+      const int e = u & 1, cur = (u >> 1) & 1, prev = cur ^ 1;       // output m -> slot cur, output m - 1 -> slot prev
+      if (separable) {
+        float hrow[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float t = v[2 * j] * kx[0];
+#pragma unroll
+          for (int b = 1; b < 4; ++b) t = fmaf(v[2 * j + b], kx[b], t);
+          hrow[j] = t;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[cur][j] = fmaf(hrow[j], ky[e], acc[cur][j]);
+          acc[prev][j] = fmaf(hrow[j], ky[e + 2], acc[prev][j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            acc[cur][j] = fmaf(v[2 * j + b], kr[e * 4 + b], acc[cur][j]);
+            acc[prev][j] = fmaf(v[2 * j + b], kr[(e + 2) * 4 + b], acc[prev][j]);
+          }
+      }
+      if (e == 1) {                                                   // rows 2m-2 .. 2m+1 seen: output m - 1 is complete
+        const int orow = (r >> 1) - 1;
+        if (orow >= 0 && orow < RS && oy0 + orow < out_h && ox < out_w) {
+          float* dst = yp + (size_t)(oy0 + orow) * out_w + ox;
+          if (vec_store) {
+            __stcs(reinterpret_cast<float4*>(dst), make_float4(acc[prev][0], acc[prev][1], acc[prev][2], acc[prev][3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (ox + j < out_w) dst[j] = acc[prev][j];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[prev][j] = 0.f;
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
 // up = 2, down = 1, 4x4 taps, pad (2,1): the RGB-skip Upsample (model.py:35-53), out = 2 x in.  Output parity (py,px)
 // has 2x2 live taps: out[2y+py][2x+px] = sum_{a,b in {0,1}} in[y-1+py+a][x-1+px+b] * kf[py+2a][px+2b].
 // A lane owns 4 input columns (8 output columns, two float4 stores per output row) and slides a 3-row window.
@@ -410,6 +533,10 @@ int launch_upfirdn2d(const float* x, float* y, const float* k, int planes, int i
     const int wx = 1;              // warps stacked vertically (measured: 4.9 TB/s vs 4.5 side by side for 512-wide planes)
     dim3 grid(cdiv(in_w, 128 * wx), cdiv(in_h, RS * (8 / wx)), planes);
     upfirdn2d_up2_k4_strip_kernel<RS><<<grid, 256, 0, st>>>(x, y, k, in_h, in_w, wx);
+  } else if (k4 && sym && up_x == 1 && down_x == 2 && planes <= 65535 && px0 >= 0 && py0 >= 0 && px1 >= 0 && py1 >= 0) {
+    constexpr int RS = 16;                                   // 8 warps x 16 output rows x 128 output columns per CTA
+    dim3 grid(cdiv(out_w, 128), cdiv(out_h, 8 * RS), planes);
+    upfirdn2d_down2_k4_strip_kernel<RS><<<grid, 256, 0, st>>>(x, y, k, in_h, in_w, out_h, out_w, px0, py0);
   } else if (k4 && sym && up_x == 1 && (down_x == 1 || down_x == 2) && planes <= 65535) {
     if (down_x == 1) {
       dim3 grid(cdiv(out_w, 64), cdiv(out_h, 32), planes);
