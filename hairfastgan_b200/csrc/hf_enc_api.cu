@@ -132,6 +132,14 @@ int hf_stem7x7s2_nhwc16(const float* x, const void* wpacked, const float* shift,
   return launch_stem7x7s2_fused(x, wpacked, shift, y16, batch, height, width, dtype, (cudaStream_t)stream);
 }
 
+int hf_stem3x3_nhwc16(const float* x, const void* wpacked, const float* shift, const float* slope, const float* s2,
+                      const float* b2, void* y16, void* y16b, int batch, int height, int width, int dtype, void* stream) {
+  int rc = ensure_device_current();
+  if (rc) return rc;
+  return launch_stem3x3_fused(x, wpacked, shift, slope, s2, b2, y16, y16b, batch, height, width, dtype,
+                              (cudaStream_t)stream);
+}
+
 int hf_im2col7x7s2_nhwc16(const float* x, void* y16, int batch, int height, int width, int dtype, void* stream) {
   int rc = ensure_device_current();
   if (rc) return rc;

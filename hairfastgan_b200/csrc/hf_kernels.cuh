@@ -64,6 +64,8 @@ int launch_channel_partial(const void* x16, float* ws, int B, int HW, int C, int
 int launch_im2col7x7s2(const float* x, void* y16, int B, int H, int W, int dtype, cudaStream_t st);
 int launch_stem7x7s2_fused(const float* x, const void* wpacked, const float* shift, void* y16, int B, int H, int W,
                            int dtype, cudaStream_t st);
+int launch_stem3x3_fused(const float* x, const void* wpacked, const float* shift, const float* slope, const float* s2,
+                         const float* b2, void* y16, void* y16b, int B, int H, int W, int dtype, cudaStream_t st);
 int launch_maxpool3x3s2(const void* x16, void* y16, int B, int H, int W, int C, int dtype, cudaStream_t st);
 int launch_pooled_fc(const void* x16, const float* w, const float* scale, const float* shift, int act, float* out,
                      float* ws, int B, int HW, int C, int Cout, int dtype, cudaStream_t st);

@@ -389,6 +389,137 @@ __global__ void __launch_bounds__(256, 2) stem7x7s2_fused_kernel(const float* __
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused 3x3 RGB stem of the IR-SE / iresnet encoders (round 2): Conv2d(3, 64, 3, 1, 1) + BatchNorm + PReLU
+// (encoder4editing/models/encoders/psp_encoders.py:176-178 `input_layer`; FeatureStyleEncoder/arcface/iresnet.py:92-95
+// conv1/bn1/prelu as taken by nets/feature_style_encoder.py:27; models/Net.py:347) in ONE kernel: fp32 NCHW image in,
+// the raw 16-bit NHWC [B,H,W,64] activation AND its BatchNorm-affined copy for the first block out.  It replaces an
+// NCHW->NHWC(32) layout pass plus a tcgen05 convolution whose K = 9 x 32 was 90 % zero padding (Cin 3 -> 32).  Same
+// scheme as the 7x7 stem above (HBM-bound: 0.8 MB in, 16.8 MB out per 256^2 image): window gathered in shared memory
+// interleaved [row][x*4 + c] (c = 3 is a zero lane so that every k pair is one aligned 32-bit word), k = ky*16 + kx*4 + c
+// (K = 48), mma.sync fragments, persistent CTAs with the 7 KB of packed weights resident.
+// ------------------------------------------------------------------------------------------------
+constexpr int kS3InRows = kSfRows + 2, kS3InPitch = (kSfCols + 2) * 4;       // 10 rows x 136 elements
+constexpr int kS3K = 48, kS3WPitch = 56;
+
+template <int DT>
+__global__ void __launch_bounds__(256, 2) stem3x3_fused_kernel(const float* __restrict__ x,
+                                                               const uint16_t* __restrict__ wp,
+                                                               const float* __restrict__ shift,
+                                                               const float* __restrict__ slope,
+                                                               const float* __restrict__ s2,
+                                                               const float* __restrict__ b2,
+                                                               uint16_t* __restrict__ y, uint16_t* __restrict__ yb,
+                                                               int H, int W, int tiles_x, int tiles_y, int total_tiles) {
+  __shared__ __align__(16) uint16_t w_s[64 * kS3WPitch];
+  __shared__ __align__(16) uint16_t in_s[kS3InRows * kS3InPitch + 16];
+  __shared__ __align__(16) uint16_t out_s[256 * 64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 64 * kS3WPitch / 8; i += 256)
+    reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(wp) + i);
+  for (int i = threadIdx.x; i < kS3InRows * kS3InPitch + 16; i += 256) in_s[i] = 0;      // the c = 3 lanes stay zero
+  const int g4 = lane >> 2, q2 = (lane & 3) * 2;
+  __syncthreads();
+
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x, t2 = tile / tiles_x, ty = t2 % tiles_y, b = t2 / tiles_y;
+    const int oy0 = ty * kSfRows, ox0 = tx * kSfCols;
+    const float* xb = x + (size_t)b * 3 * H * W;
+    // ---- stage the 10 x 34 x 3 window (zero outside the image = the conv padding)
+    for (int i = threadIdx.x; i < 3 * kS3InRows * (kSfCols + 2); i += 256) {
+      const int cx = i % (kSfCols + 2), t = i / (kSfCols + 2), r = t % kS3InRows, c = t / kS3InRows;
+      const int gy = oy0 - 1 + r, gx = ox0 - 1 + cx;
+      const float v = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(xb + ((size_t)c * H + gy) * W + gx) : 0.f;
+      in_s[r * kS3InPitch + cx * 4 + c] = Half2T<DT>::one(v);
+    }
+    __syncthreads();
+    float acc[2][8][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < kS3K / 16; ++ks) {            // ks = kernel row ky
+      const uint16_t* a_row = in_s + (warp + ks) * kS3InPitch;
+      uint32_t a[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int oxa = i * 16 + g4;
+        a[i][0] = *reinterpret_cast<const uint32_t*>(a_row + 4 * oxa + q2);
+        a[i][1] = *reinterpret_cast<const uint32_t*>(a_row + 4 * (oxa + 8) + q2);
+        a[i][2] = *reinterpret_cast<const uint32_t*>(a_row + 4 * oxa + q2 + 8);
+        a[i][3] = *reinterpret_cast<const uint32_t*>(a_row + 4 * (oxa + 8) + q2 + 8);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t bf[2];
+        const uint16_t* wrow = w_s + (j * 8 + g4) * kS3WPitch + ks * 16 + q2;
+        bf[0] = *reinterpret_cast<const uint32_t*>(wrow);
+        bf[1] = *reinterpret_cast<const uint32_t*>(wrow + 8);
+        mma16816<DT>(acc[0][j], a[0], bf);
+        mma16816<DT>(acc[1][j], a[1], bf);
+      }
+    }
+    // ---- epilogue: v = prelu(acc + shift); pass 0 stores v, pass 1 stores v * s2 + b2 (the first block's BatchNorm)
+    for (int pass = 0; pass < (yb ? 2 : 1); ++pass) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int n0 = j * 8 + q2;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int pix = warp * 32 + i * 16 + g4 + 8 * h;
+            float v[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              float t = acc[i][j][2 * h + u] + __ldg(shift + n0 + u);
+              t = t > 0.f ? t : t * __ldg(slope + n0 + u);
+              if (pass) t = fmaf(t, __ldg(s2 + n0 + u), __ldg(b2 + n0 + u));
+              v[u] = t;
+            }
+            *reinterpret_cast<uint32_t*>(out_s + pix * 64 + ((j ^ (pix & 7)) * 8) + q2) = Half2T<DT>::pack(v[0], v[1]);
+          }
+        }
+      __syncthreads();
+      uint16_t* dst = pass ? yb : y;
+      for (int i = threadIdx.x; i < 256 * 8; i += 256) {
+        const int pix = i >> 3, ch = i & 7;
+        const int oy = oy0 + (pix >> 5), ox = ox0 + (pix & 31);
+        if (oy < H && ox < W) {
+          const uint4 v = *reinterpret_cast<const uint4*>(out_s + pix * 64 + ((ch ^ (pix & 7)) * 8));
+          *reinterpret_cast<uint4*>(dst + (((size_t)b * H + oy) * W + ox) * 64 + ch * 8) = v;
+        }
+      }
+      __syncthreads();                                   // out_s (and, after the last pass, in_s) may be rewritten
+    }
+  }
+}
+
+int launch_stem3x3_fused(const float* x, const void* wpacked, const float* shift, const float* slope, const float* s2,
+                         const float* b2, void* y16, void* y16b, int B, int H, int W, int dtype, cudaStream_t st) {
+  HF_REQUIRE(x && wpacked && shift && slope && y16, "stem3x3: null pointer");
+  HF_REQUIRE((y16b == nullptr) == (s2 == nullptr) && (s2 == nullptr) == (b2 == nullptr),
+             "stem3x3: y16b, s2 and b2 come together");
+  HF_REQUIRE(B > 0 && H > 0 && W > 0, "stem3x3: bad shape");
+  HF_REQUIRE((((uintptr_t)wpacked | (uintptr_t)y16 | (uintptr_t)y16b) & 15) == 0, "stem3x3: buffers must be 16-byte aligned");
+  const int tiles_x = cdiv_s(W, kSfCols), tiles_y = cdiv_s(H, kSfRows);
+  const int64_t total = (int64_t)tiles_x * tiles_y * B;
+  HF_REQUIRE(total < (int64_t)2000000000, "stem3x3: too many tiles");
+  const int grid = (int)std::min<int64_t>(total, (int64_t)num_sms() * 2);
+  if (dtype == HF_BF16)
+    stem3x3_fused_kernel<HF_BF16><<<grid, 256, 0, st>>>(x, (const uint16_t*)wpacked, shift, slope, s2, b2, (uint16_t*)y16,
+                                                        (uint16_t*)y16b, H, W, tiles_x, tiles_y, (int)total);
+  else
+    stem3x3_fused_kernel<HF_F16><<<grid, 256, 0, st>>>(x, (const uint16_t*)wpacked, shift, slope, s2, b2, (uint16_t*)y16,
+                                                       (uint16_t*)y16b, H, W, tiles_x, tiles_y, (int)total);
+  HF_LAUNCH_OK("stem3x3_fused");
+  count_launch();
+  return HF_OK;
+}
+
 int launch_stem7x7s2_fused(const float* x, const void* wpacked, const float* shift, void* y16, int B, int H, int W,
                            int dtype, cudaStream_t st) {
   HF_REQUIRE(x && wpacked && shift && y16, "stem7x7s2: null pointer");

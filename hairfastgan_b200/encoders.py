@@ -218,10 +218,8 @@ class Encoder4Editing(_PackCacheMixin, nn.Module):
         if self._pk is not None and self._pk["key"] == key:
             return self._pk
         il = self.input_layer
-        sc, sh = nn16.bn_affine(il[1])
         pk = {"key": key,
-              "stem": nn16.PackedConv2d(il[0].weight, sc, cin_pad=32), "stem_shift": sh,
-              "stem_slope": il[2].weight.detach().float().contiguous(),
+              "stem": nn16.PackedStem3x3(il[0].weight, il[1], il[2].weight),      # conv + BN + PReLU, one fused kernel
               "blocks": [m.packed() for m in self.body],
               "lat1": nn16.PackedConv2d(self.latlayer1.weight), "lat2": nn16.PackedConv2d(self.latlayer2.weight),
               "heads": [_PackedHeads(list(self.styles[:self.coarse_ind])),
@@ -241,8 +239,7 @@ class Encoder4Editing(_PackCacheMixin, nn.Module):
     def _forward_impl(self, x):
         pk = self._pack()
         blocks = pk["blocks"]
-        x16 = nn16.to_nhwc16(x, c_pad=32)
-        raw, bn, _ = pk["stem"](x16, shift=pk["stem_shift"], act=1, slope=pk["stem_slope"], y16b_affine=blocks[0].pre)
+        raw, bn = pk["stem"](x, y16b_affine=blocks[0].pre)
         taps = {}
         for i, blk in enumerate(blocks):
             nxt = blocks[i + 1].pre if i + 1 < len(blocks) else None
@@ -366,7 +363,6 @@ class fs_encoder_v2(_PackCacheMixin, nn.Module):
         key = _params_key(self)
         if self._pk is not None and self._pk["key"] == key:
             return self._pk
-        sc, sh = nn16.bn_affine(self.conv[1])
         branches = []
         for cl, stride in zip(self._content_branches(), self._content_strides):
             c_mid_scale, c_mid_shift = nn16.bn_affine(cl[2])
@@ -376,8 +372,7 @@ class fs_encoder_v2(_PackCacheMixin, nn.Module):
                              "slope": cl[3].weight.detach().float().contiguous(),
                              "conv2": nn16.PackedConv2d(cl[4].weight, c_out_scale, stride=stride),
                              "shift2": c_out_shift})
-        pk = {"key": key, "stem": nn16.PackedConv2d(self.conv[0].weight, sc, cin_pad=32), "stem_shift": sh,
-              "stem_slope": self.conv[2].weight.detach().float().contiguous(),
+        pk = {"key": key, "stem": nn16.PackedStem3x3(self.conv[0].weight, self.conv[1], self.conv[2].weight),
               "stages": [[b.packed() for b in blk] for blk in (self.block_1, self.block_2, self.block_3, self.block_4)],
               "content": branches,
               # the n_styles nn.Linear(960*9, 512) heads (feature_style_encoder.py:44-45,62-64) stacked: ONE 1x1
@@ -401,8 +396,7 @@ class fs_encoder_v2(_PackCacheMixin, nn.Module):
         for st in pk["stages"]:
             n += len(st)
             ends.append(n - 1)
-        x16 = nn16.to_nhwc16(x, c_pad=32)
-        raw, bn, _ = pk["stem"](x16, shift=pk["stem_shift"], act=1, slope=pk["stem_slope"], y16b_affine=blocks[0].pre)
+        raw, bn = pk["stem"](x, y16b_affine=blocks[0].pre)
         feats, content = [], []
         for i, blk in enumerate(blocks):
             nxt = blocks[i + 1].pre if i + 1 < len(blocks) else None

@@ -210,6 +210,47 @@ class PackedStem7x7:
         return y
 
 
+class PackedStem3x3:
+    """Conv2d(3, 64, 3, 1, 1) + eval BatchNorm + PReLU of the IR-SE / iresnet encoders (psp_encoders.py:176-178,
+    arcface/iresnet.py:92-95) as ONE fused kernel (`hf_stem3x3_nhwc16`): fp32 NCHW image in, the raw 16-bit NHWC
+    activation and (optionally) its BatchNorm-affined copy for the first residual block out.  Packed weights: 16-bit
+    [64][56], k = ky*16 + kx*4 + c, BatchNorm scale folded in."""
+
+    def __init__(self, weight: torch.Tensor, bn: torch.nn.BatchNorm2d, prelu_weight: torch.Tensor,
+                 dtype: Optional[int] = None):
+        self.dtype = default_dtype() if dtype is None else dtype
+        w = _f32(weight)
+        if tuple(w.shape) != (64, 3, 3, 3):
+            raise NotImplementedError(f"stem3x3: expected a [64,3,3,3] weight, got {list(w.shape)}")
+        scale, self.shift = bn_affine(bn)
+        self.slope = _f32(prelu_weight).reshape(-1)
+        if self.slope.numel() != 64:
+            raise NotImplementedError("stem3x3: per-channel PReLU (64 slopes) expected")
+        wk = (w * scale.view(-1, 1, 1, 1)).permute(0, 2, 3, 1)                   # [n][ky][kx][c]
+        packed = torch.zeros(64, 56, device=w.device, dtype=torch.float32)
+        packed[:, :48].view(64, 3, 4, 4)[:, :, :3, :3] = wk
+        self.wp = packed.to(torch_dtype(self.dtype)).contiguous()
+
+    def __call__(self, x: torch.Tensor, y16b_affine=None):
+        """[B,3,H,W] fp32 NCHW -> (y16, y16b | None), both [B,H,W,64] 16-bit NHWC."""
+        if not x.is_cuda:
+            raise RuntimeError("stem3x3: input must be a CUDA tensor (no CPU fallback)")
+        xf = _f32(x)
+        b, c, h, w = xf.shape
+        if c != 3:
+            raise ValueError("stem3x3: expected a 3-channel image")
+        y = torch.empty(b, h, w, 64, device=x.device, dtype=torch_dtype(self.dtype))
+        yb = s2 = b2 = None
+        if y16b_affine is not None:
+            s2, b2 = _f32(y16b_affine[0]), _f32(y16b_affine[1])
+            yb = torch.empty_like(y)
+        _lib.use_device(x.device.index)
+        _lib.check(_lib.lib().hf_stem3x3_nhwc16(xf.data_ptr(), self.wp.data_ptr(), self.shift.data_ptr(),
+                                                self.slope.data_ptr(), _p(s2), _p(b2), y.data_ptr(), _p(yb), b, h, w,
+                                                self.dtype, _lib.stream_ptr()), "hf_stem3x3_nhwc16")
+        return y, yb
+
+
 def stem7x7s2(x: torch.Tensor, weight: torch.Tensor, bn: torch.nn.BatchNorm2d, dtype: Optional[int] = None):
     return PackedStem7x7(weight, bn, dtype)(x)
 

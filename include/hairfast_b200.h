@@ -259,6 +259,14 @@ int hf_adaptive_avgpool_nhwc16(const void* x16, float* y, int batch, int height,
                                int ow, int dtype, void* stream);
 
 /* ---- BiSeNet face parsing (models/CtrlHair/external_code/face_parsing/{model,resnet}.py) ---- */
+/* 3x3 RGB stem of the IR-SE / iresnet encoders fused: Conv2d(3,64,3,1,1) + eval BatchNorm + PReLU
+ * (psp_encoders.py:176-178 input_layer; arcface/iresnet.py:92-95 conv1/bn1/prelu).  x [B,3,H,W] fp32 NCHW ->
+ * y16 [B,H,W,64] = prelu(conv*bn_scale + shift) and, when y16b != NULL, y16b = y16 * s2[c] + b2[c] (the first block's
+ * leading BatchNorm), both 16-bit NHWC.  wpacked: 16-bit [64][56], row n = weight[n,c,ky,kx] * bn_scale[n] at
+ * k = ky*16 + kx*4 + c (c < 3, kx < 3), zero elsewhere; shift / slope / s2 / b2: [64] fp32. */
+int hf_stem3x3_nhwc16(const float* x, const void* wpacked, const float* shift, const float* slope, const float* s2,
+                      const float* b2, void* y16, void* y16b, int batch, int height, int width, int dtype, void* stream);
+
 /* Resnet18.conv1 7x7/s2/p3 + bn1 + ReLU fused (face_parsing/resnet.py:60-61,69-70): x [B,3,H,W] fp32 NCHW ->
  * y16 [B,(H+1)/2,(W+1)/2,64] 16-bit NHWC.  wpacked: 16-bit [64][184], row n = weight[n,c,ky,kx] * bn_scale[n] at
  * k = ky*24 + kx*3 + c (k < 168, kx*3+c < 21), zero elsewhere; shift [64] fp32 = the BatchNorm shift. */
