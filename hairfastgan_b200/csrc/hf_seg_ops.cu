@@ -309,18 +309,30 @@ __global__ void __launch_bounds__(256, 2) stem7x7s2_fused_kernel(const float* __
     const float* xb = x + (size_t)b * 3 * H * W;
     // ---- stage the 22 x 72 x 3 input window (zero outside the image = the conv padding), interleaved [row][x*3 + c]
     const int gy0 = 2 * oy0 - 3, gx0 = 2 * ox0 - 3;
+    {
+      // columns fc (0..63) of rows fr, fr+4, ..., fr+20: six loads per channel in flight before the first store;
+      // then the 8 tail columns 64..71 (threads with fc < 8)
+      const int gxa = gx0 + fc, gxb = gx0 + 64 + fc;
+      const bool cola = gxa >= 0 && gxa < W, colb = fc < 8 && gxb >= 0 && gxb < W;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float* xc = xb + (size_t)c * H * W;
-      for (int r = fr; r < kSfInRows; r += 4) {
-        const int gy = gy0 + r;
-        const bool row_ok = gy >= 0 && gy < H;
-        const float* xr = xc + (size_t)(row_ok ? gy : 0) * W;
+      for (int c = 0; c < 3; ++c) {
+        const float* xc = xb + (size_t)c * H * W;
+        float va[6], vb[6];
 #pragma unroll
-        for (int cx = fc; cx < 72; cx += 64) {
-          const int gx = gx0 + cx;
-          const float v = (row_ok && gx >= 0 && gx < W) ? __ldg(xr + gx) : 0.f;
-          in_s[r * kSfInPitch + cx * 3 + c] = Half2T<DT>::one(v);
+        for (int kk = 0; kk < 6; ++kk) {
+          const int r = fr + 4 * kk, gy = gy0 + r;
+          const bool row_ok = r < kSfInRows && gy >= 0 && gy < H;
+          const float* xr = xc + (size_t)(row_ok ? gy : 0) * W;
+          va[kk] = (row_ok && cola) ? __ldg(xr + gxa) : 0.f;
+          vb[kk] = (row_ok && colb) ? __ldg(xr + gxb) : 0.f;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 6; ++kk) {
+          const int r = fr + 4 * kk;
+          if (r < kSfInRows) {
+            in_s[r * kSfInPitch + fc * 3 + c] = Half2T<DT>::one(va[kk]);
+            if (fc < 8) in_s[r * kSfInPitch + (64 + fc) * 3 + c] = Half2T<DT>::one(vb[kk]);
+          }
         }
       }
     }
@@ -414,11 +426,19 @@ __global__ void __launch_bounds__(256, 2) stem3x3_fused_kernel(const float* __re
   __shared__ __align__(16) uint16_t w_s[64 * kS3WPitch];
   __shared__ __align__(16) uint16_t in_s[kS3InRows * kS3InPitch + 16];
   __shared__ __align__(16) uint16_t out_s[256 * 64];
+  __shared__ float ep_s[4][64];                          // shift, slope, s2, b2
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 64 * kS3WPitch / 8; i += 256)
     reinterpret_cast<uint4*>(w_s)[i] = __ldg(reinterpret_cast<const uint4*>(wp) + i);
   for (int i = threadIdx.x; i < kS3InRows * kS3InPitch + 16; i += 256) in_s[i] = 0;      // the c = 3 lanes stay zero
+  if (threadIdx.x < 64) {
+    ep_s[0][threadIdx.x] = __ldg(shift + threadIdx.x);
+    ep_s[1][threadIdx.x] = __ldg(slope + threadIdx.x);
+    ep_s[2][threadIdx.x] = s2 ? __ldg(s2 + threadIdx.x) : 1.f;
+    ep_s[3][threadIdx.x] = b2 ? __ldg(b2 + threadIdx.x) : 0.f;
+  }
   const int g4 = lane >> 2, q2 = (lane & 3) * 2;
+  const int fcx = threadIdx.x % (kSfCols + 2), fr0 = threadIdx.x / (kSfCols + 2);         // fill: 7 rows x 34 columns per pass
   __syncthreads();
 
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -426,11 +446,24 @@ __global__ void __launch_bounds__(256, 2) stem3x3_fused_kernel(const float* __re
     const int oy0 = ty * kSfRows, ox0 = tx * kSfCols;
     const float* xb = x + (size_t)b * 3 * H * W;
     // ---- stage the 10 x 34 x 3 window (zero outside the image = the conv padding)
-    for (int i = threadIdx.x; i < 3 * kS3InRows * (kSfCols + 2); i += 256) {
-      const int cx = i % (kSfCols + 2), t = i / (kSfCols + 2), r = t % kS3InRows, c = t / kS3InRows;
-      const int gy = oy0 - 1 + r, gx = ox0 - 1 + cx;
-      const float v = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(xb + ((size_t)c * H + gy) * W + gx) : 0.f;
-      in_s[r * kS3InPitch + cx * 4 + c] = Half2T<DT>::one(v);
+    if (fr0 < 7) {
+      const int gx = ox0 - 1 + fcx;
+      const bool col_ok = gx >= 0 && gx < W;
+      float v[3][2];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {                    // rows fr0 and fr0 + 7: all six loads in flight together
+          const int r = fr0 + 7 * k, gy = oy0 - 1 + r;
+          v[c][k] = (r < kS3InRows && col_ok && gy >= 0 && gy < H) ? __ldg(xb + ((size_t)c * H + gy) * W + gx) : 0.f;
+        }
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int r = fr0 + 7 * k;
+          if (r < kS3InRows) in_s[r * kS3InPitch + fcx * 4 + c] = Half2T<DT>::one(v[c][k]);
+        }
     }
     __syncthreads();
     float acc[2][8][4];
@@ -475,9 +508,9 @@ __global__ void __launch_bounds__(256, 2) stem3x3_fused_kernel(const float* __re
             float v[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              float t = acc[i][j][2 * h + u] + __ldg(shift + n0 + u);
-              t = t > 0.f ? t : t * __ldg(slope + n0 + u);
-              if (pass) t = fmaf(t, __ldg(s2 + n0 + u), __ldg(b2 + n0 + u));
+              float t = acc[i][j][2 * h + u] + ep_s[0][n0 + u];
+              t = t > 0.f ? t : t * ep_s[1][n0 + u];
+              if (pass) t = fmaf(t, ep_s[2][n0 + u], ep_s[3][n0 + u]);
               v[u] = t;
             }
             *reinterpret_cast<uint32_t*>(out_s + pix * 64 + ((j ^ (pix & 7)) * 8) + q2) = Half2T<DT>::pack(v[0], v[1]);

@@ -295,3 +295,27 @@ def test_cuda_graph_replay_matches_eager(N):
     seg = seg.cuda()
     lab = [seg.parse_labels(x[:1]) for _ in range(3)]
     assert all(torch.equal(lab[0], o) for o in lab[1:]) and torch.equal(lab[0], seg(x[:1])[0].argmax(1))
+
+
+def test_fused_stem3x3_vs_torch(N):
+    """hf_stem3x3_nhwc16: Conv2d(3,64,3,1,1) + eval BatchNorm + PReLU (+ the next block's BatchNorm as second output)
+    against torch fp32, on a size that is not a multiple of the 8 x 32 tile."""
+    g = torch.Generator().manual_seed(77)
+    x = torch.rand(2, 3, 40, 72, generator=g) * 2 - 1
+    conv = torch.nn.Conv2d(3, 64, 3, 1, 1, bias=False)
+    conv.weight.data = torch.randn(64, 3, 3, 3, generator=g) * 0.3
+    bn = torch.nn.BatchNorm2d(64).eval()
+    bn.weight.data.uniform_(0.5, 1.5, generator=g); bn.bias.data.normal_(0, 0.2, generator=g)
+    bn.running_mean.normal_(0, 0.2, generator=g); bn.running_var.uniform_(0.5, 1.5, generator=g)
+    prelu = torch.nn.PReLU(64)
+    prelu.weight.data.uniform_(0.05, 0.5, generator=g)
+    s2, b2 = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.3
+    ref = prelu(bn(conv(x)))
+    refb = ref * s2.view(1, -1, 1, 1) + b2.view(1, -1, 1, 1)
+    stem = N.PackedStem3x3(conv.weight.cuda(), bn.cuda(), prelu.weight.cuda())
+    y16, y16b = stem(x.cuda(), y16b_affine=(s2.cuda(), b2.cuda()))
+    assert y16.shape == (2, 40, 72, 64) and y16b.shape == (2, 40, 72, 64)
+    e, eb = rel_err(N.to_nchw32(y16), ref)[0], rel_err(N.to_nchw32(y16b), refb)[0]
+    assert e < TOL_CONV[dtype_name()] and eb < TOL_CONV[dtype_name()] * 1.5, (e, eb)
+    y_only, none = stem(x.cuda())
+    assert none is None and torch.equal(y_only, y16)
