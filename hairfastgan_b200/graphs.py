@@ -114,9 +114,12 @@ def run_multi(owner, tag, pack_key, fn, xs, batch: int, uses_rng: bool = False):
         try:
             ent = cache[sig] = _capture(fn, [None if x is None else x.contiguous() for x in xs], pack_key, uses_rng)
             _STATS["captures"] += 1
-        except Exception:                               # noqa: BLE001 -- not capturable here: stay eager for this signature
+        except Exception as exc:                        # noqa: BLE001 -- not capturable here: stay eager for this signature
             cache[sig] = False
             _STATS["failed"] += 1
+            import warnings
+            warnings.warn(f"hairfastgan_b200.graphs: CUDA-graph capture of {tag!r} failed ({exc!r}); this signature "
+                          "stays on the eager CUDA path", RuntimeWarning, stacklevel=2)
             torch.cuda.synchronize(first.device)
             return fn(*xs)
     for st, x in zip(ent.static_in, xs):
