@@ -282,6 +282,307 @@ __global__ void __launch_bounds__(256) upfirdn2d_up1_k4_strip_kernel(const float
   cp_async_wait<0>();
 }
 
+// up = 1, down in {1, 2}, 4x4 taps, pads 0..3, planes up to 1040 columns wide: the input side done by the TMA engine.
+// A strip of full-width rows of one plane is ONE contiguous span of global memory, so although its rows are only
+// 4-byte aligned (width 2R+1 after the transposed convolution) the span can be fetched with 1-D bulk copies
+// (`cp.async.bulk`, 16-byte aligned start and size: the span is widened to the enclosing 16-byte boundaries, which
+// stay inside the tensor because the launch checks base alignment and total size).  One elected thread keeps up to
+// S chunks of CR rows in flight per CTA (mbarrier complete_tx); there are no per-element copy instructions and no
+// per-element address arithmetic -- the cp.async ring above spends 36 instructions per output on that, this kernel
+// ~14 -- and the small stages (3 x 16 KB at 1025 columns) leave room for 4 CTAs per SM, which is what the HBM rate
+// turned out to depend on (measured on the [256,1025,1025] blur: 8-row chunks x 3, 2 CTAs/SM 5.0 TB/s; 4-row chunks
+// x 3, 4 CTAs/SM 6.1 TB/s = 0.93 of the copy peak; ring kernel 4.45).  A thread owns the output columns t, t+256, ...
+// (conflict-free 4-byte LDS whatever the row's alignment; 2-way for down = 2) and walks down the strip with the
+// separable (or general) FIR in registers exactly like the ring kernels; padding columns are handled by a masked path
+// that only the threads owning an edge column take, padding rows contribute nothing and are never fetched.
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_s, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_s), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+// Rows [lo, hi) of the plane that chunk c of a strip holds (strip row r = input row iy0 + r, nrows rows, CR per chunk)
+// and the 16-byte aligned global byte span [a0, a0 + bytes) that contains them.
+struct BulkSpan {
+  int lo, hi;
+  size_t a0;
+  uint32_t bytes;
+};
+__device__ __forceinline__ BulkSpan bulk_span(int c, int CR, int iy0, int nrows, int in_h, int in_w, size_t plane_off) {
+  BulkSpan sp;
+  sp.lo = max(iy0 + c * CR, 0);
+  sp.hi = min(iy0 + min((c + 1) * CR, nrows), in_h);
+  const size_t g0 = (plane_off + (size_t)sp.lo * in_w) * 4, g1 = (plane_off + (size_t)max(sp.hi, sp.lo) * in_w) * 4;
+  sp.a0 = g0 & ~(size_t)15;
+  sp.bytes = (uint32_t)(((g1 + 15) & ~(size_t)15) - sp.a0);
+  return sp;
+}
+
+template <int DOWN, int NC, int RS, int CR, int S>            // RS output rows per CTA, CR input rows per chunk, S stages
+__global__ void __launch_bounds__(256) upfirdn2d_k4_bulk_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                const float* __restrict__ k, int in_h, int in_w,
+                                                                int out_h, int out_w, int px0, int py0,
+                                                                uint32_t stage_bytes) {
+  static_assert(CR % 4 == 0 && (DOWN == 1 || DOWN == 2), "chunk rows keep the accumulator rotation static");
+  constexpr int HALO = DOWN == 1 ? 3 : 2;
+  constexpr int NACC = DOWN == 1 ? 4 : 2;
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  __shared__ uint64_t full[S];
+  const int t = threadIdx.x;
+  const int oy0 = blockIdx.y * RS;
+  float kr[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kr[i] = __ldg(k + 15 - i);           // flipped taps: kr[a*4+b] = k[3-a][3-b]
+  float kx[4], ky[4];
+  bool separable = kr[0] != 0.f;                                      // rank-1 test, as in the ring kernels
+#pragma unroll
+  for (int b = 0; b < 4; ++b) kx[b] = kr[b];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) ky[a] = separable ? kr[a * 4] / kr[0] : 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      separable = separable && fabsf(ky[a] * kx[b] - kr[a * 4 + b]) <= 1e-6f * fabsf(kr[a * 4 + b]) + 1e-30f;
+  const size_t plane_off = (size_t)blockIdx.z * in_h * in_w;          // elements
+  float* yp = y + (size_t)blockIdx.z * out_h * out_w;
+  const int nrows = DOWN * min(RS, out_h - oy0) + HALO;               // strip rows that feed a stored output row
+  const int nchunks = (nrows + CR - 1) / CR;
+  const int iy0 = DOWN * oy0 - py0;                                   // input row of strip row 0 (>= -3)
+  const uint32_t smem_s = smem_u32(bulk_smem);
+  auto issue_chunk = [&](int c) {                                     // one thread
+    const BulkSpan sp = bulk_span(c, CR, iy0, nrows, in_h, in_w, plane_off);
+    if (sp.lo >= sp.hi) return;                                       // only trailing chunks can be empty
+    const int s = c % S;
+    mbar_expect_tx(&full[s], sp.bytes);
+    bulk_load_1d(smem_s + (uint32_t)s * stage_bytes, reinterpret_cast<const unsigned char*>(x) + sp.a0, sp.bytes,
+                 &full[s]);
+  };
+  if (t == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (t == 0)
+    for (int c = 0; c < S && c < nchunks; ++c) issue_chunk(c);
+
+  // column state (row-invariant): byte offset of tap 0 inside a row; edge columns take the masked path
+  uint32_t off[NC];
+  uint32_t edge = 0, live = 0;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    const int ox = t + 256 * j, ix = DOWN * ox - px0;
+    const bool in_img = ox < out_w;
+    const bool inside = ix >= 0 && ix + 3 < in_w;
+    off[j] = (in_img && inside) ? (uint32_t)ix * 4u : 0u;
+    if (in_img) live |= 1u << j;
+    if (in_img && !inside) edge |= 1u << j;
+  }
+  float acc[NACC][NC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i)
+#pragma unroll
+    for (int j = 0; j < NC; ++j) acc[i][j] = 0.f;
+
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    const BulkSpan sp = bulk_span(c, CR, iy0, nrows, in_h, in_w, plane_off);
+    const int s = c % S;
+    if (sp.lo < sp.hi) mbar_wait(&full[s], (uint32_t)(c / S) & 1u);
+    const uint32_t stage_s = smem_s + (uint32_t)s * stage_bytes;
+#pragma unroll
+    for (int u8 = 0; u8 < CR; ++u8) {
+      const int r = c * CR + u8;
+      if (r < nrows) {                                                 // block-uniform
+        const int iy = iy0 + r;
+        const bool row_ok = iy >= sp.lo && iy < sp.hi;                 // block-uniform: padding rows add nothing
+        // DOWN 1: input row r feeds output rows r - a (tap row a), slot (r - a) & 3.  DOWN 2: r = 2m + e feeds output
+        // m (tap row e, slot cur) and m - 1 (tap row e + 2, slot prev).  Static because chunks start at multiples of 4.
+        const int u = u8 & 3, e = u8 & 1, cur = (u8 >> 1) & 1, prev = cur ^ 1;
+        if (row_ok) {
+          const uint32_t row_s = stage_s + (uint32_t)((plane_off + (size_t)iy * in_w) * 4 - sp.a0);
+          float v[NC][4];
+#pragma unroll
+          for (int j = 0; j < NC; ++j) {
+            if (edge & (1u << j)) {                                    // a padding column inside this window
+              const int ix = DOWN * (t + 256 * j) - px0;
+#pragma unroll
+              for (int b = 0; b < 4; ++b)
+                v[j][b] = (ix + b >= 0 && ix + b < in_w) ? lds_f32(row_s + (uint32_t)(ix + b) * 4u) : 0.f;
+            } else {
+#pragma unroll
+              for (int b = 0; b < 4; ++b) v[j][b] = lds_f32(row_s + off[j] + 4u * b);
+            }
+          }
+          if (separable) {
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+              float h = v[j][0] * kx[0];
+#pragma unroll
+              for (int b = 1; b < 4; ++b) h = fmaf(v[j][b], kx[b], h);
+              if constexpr (DOWN == 1) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) acc[(u - a) & 3][j] = fmaf(h, ky[a], acc[(u - a) & 3][j]);
+              } else {
+                acc[cur][j] = fmaf(h, ky[e], acc[cur][j]);
+                acc[prev][j] = fmaf(h, ky[e + 2], acc[prev][j]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < NC; ++j)
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                if constexpr (DOWN == 1) {
+#pragma unroll
+                  for (int a = 0; a < 4; ++a) acc[(u - a) & 3][j] = fmaf(v[j][b], kr[a * 4 + b], acc[(u - a) & 3][j]);
+                } else {
+                  acc[cur][j] = fmaf(v[j][b], kr[e * 4 + b], acc[cur][j]);
+                  acc[prev][j] = fmaf(v[j][b], kr[(e + 2) * 4 + b], acc[prev][j]);
+                }
+              }
+          }
+        }
+        // the output row that is complete once this input row has been added (row counts bound it by nrows)
+        const int orow = DOWN == 1 ? r - 3 : (r >> 1) - 1;
+        const int slot = DOWN == 1 ? (u + 1) & 3 : prev;
+        if (DOWN == 1 || e == 1) {
+          if (orow >= 0) {
+            float* dst = yp + (size_t)(oy0 + orow) * out_w + t;
+#pragma unroll
+            for (int j = 0; j < NC; ++j)
+              if (live & (1u << j)) __stcs(dst + 256 * j, acc[slot][j]);
+          }
+#pragma unroll
+          for (int j = 0; j < NC; ++j) acc[slot][j] = 0.f;
+        }
+      }
+    }
+    __syncthreads();                                                   // every thread is done with stage s
+    if (t == 0 && c + S < nchunks) issue_chunk(c + S);
+  }
+}
+
+// up = 2, down = 1, 4x4 taps, pad (2,1) (the RGB-skip Upsample) with the same TMA-fed strips: a thread owns the input
+// columns t, t+256, ... and slides a 3-row x 3-column window; every input pixel yields a 2x2 output quad, stored as
+// two 8-byte pairs (a warp writes 256 contiguous bytes per store).  Chunks are a multiple of 3 rows so that the
+// window rotation is static.
+template <int NC, int RS, int CR, int S>                      // RS INPUT rows per CTA
+__global__ void __launch_bounds__(256) upfirdn2d_up2_k4_bulk_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                    const float* __restrict__ k, int in_h, int in_w,
+                                                                    uint32_t stage_bytes) {
+  static_assert(CR % 3 == 0, "chunk rows keep the window rotation static");
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  __shared__ uint64_t full[S];
+  const int t = threadIdx.x;
+  const int y0 = blockIdx.y * RS;
+  float kr[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kr[i] = __ldg(k + 15 - i);
+  const size_t plane_off = (size_t)blockIdx.z * in_h * in_w;
+  const int out_w = 2 * in_w;
+  float* yp = y + (size_t)blockIdx.z * (2 * in_h) * out_w;
+  const int nrows = min(RS, in_h - y0) + 2;                           // strip row r = input row y0 - 1 + r
+  const int nchunks = (nrows + CR - 1) / CR;
+  const int iy0 = y0 - 1;
+  const uint32_t smem_s = smem_u32(bulk_smem);
+  auto issue_chunk = [&](int c) {
+    const BulkSpan sp = bulk_span(c, CR, iy0, nrows, in_h, in_w, plane_off);
+    if (sp.lo >= sp.hi) return;
+    const int s = c % S;
+    mbar_expect_tx(&full[s], sp.bytes);
+    bulk_load_1d(smem_s + (uint32_t)s * stage_bytes, reinterpret_cast<const unsigned char*>(x) + sp.a0, sp.bytes,
+                 &full[s]);
+  };
+  if (t == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (t == 0)
+    for (int c = 0; c < S && c < nchunks; ++c) issue_chunk(c);
+  uint32_t off[NC];
+  uint32_t edge = 0, live = 0;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    const int xx = t + 256 * j;
+    const bool in_img = xx < in_w;
+    const bool inside = xx >= 1 && xx + 1 < in_w;
+    off[j] = (in_img && inside) ? (uint32_t)(xx - 1) * 4u : 0u;
+    if (in_img) live |= 1u << j;
+    if (in_img && !inside) edge |= 1u << j;
+  }
+  float win[3][NC][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) win[i][j][b] = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    const BulkSpan sp = bulk_span(c, CR, iy0, nrows, in_h, in_w, plane_off);
+    const int s = c % S;
+    if (sp.lo < sp.hi) mbar_wait(&full[s], (uint32_t)(c / S) & 1u);
+    const uint32_t stage_s = smem_s + (uint32_t)s * stage_bytes;
+#pragma unroll
+    for (int u8 = 0; u8 < CR; ++u8) {
+      const int r = c * CR + u8;
+      if (r < nrows) {
+        const int u = u8 % 3;                                          // strip row r lives in window slot r % 3 = u
+        const int iy = iy0 + r;
+        const bool row_ok = iy >= sp.lo && iy < sp.hi;
+        const uint32_t row_s = stage_s + (uint32_t)((plane_off + (size_t)(row_ok ? iy : sp.lo) * in_w) * 4 - sp.a0);
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          if (!row_ok) {
+#pragma unroll
+            for (int b = 0; b < 3; ++b) win[u][j][b] = 0.f;
+          } else if (edge & (1u << j)) {
+            const int ix = t + 256 * j - 1;
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+              win[u][j][b] = (ix + b >= 0 && ix + b < in_w) ? lds_f32(row_s + (uint32_t)(ix + b) * 4u) : 0.f;
+          } else {
+#pragma unroll
+            for (int b = 0; b < 3; ++b) win[u][j][b] = lds_f32(row_s + off[j] + 4u * b);
+          }
+        }
+        if (r >= 2) {                                                  // rows yy-1, yy, yy+1 = strip rows r-2, r-1, r
+          const int yy = y0 + r - 2;
+#pragma unroll
+          for (int py = 0; py < 2; ++py) {
+            float* dst = yp + (size_t)(2 * yy + py) * out_w + 2 * t;
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+              float o[2];
+#pragma unroll
+              for (int px = 0; px < 2; ++px) {
+                float sum = 0.f;
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                  for (int b = 0; b < 2; ++b)               // strip row r - 2 + py + a -> slot (u + 1 + py + a) % 3
+                    sum = fmaf(win[(u + 1 + py + a) % 3][j][px + b], kr[(py + 2 * a) * 4 + px + 2 * b], sum);
+                o[px] = sum;
+              }
+              if (live & (1u << j)) __stcs(reinterpret_cast<float2*>(dst + 512 * j), make_float2(o[0], o[1]));
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (t == 0 && c + S < nchunks) issue_chunk(c + S);
+  }
+}
+
 // up = 1, down = 2, 4x4 taps, pad >= 0 (the Downsample / ConvLayer blur of the reference, model.py:56-74; not on the
 // swap path): same scheme as the up1 kernel -- per-warp cp.async ring, register accumulators -- with two input rows
 // and 2 x 128 + 2 input columns per output row.  Input row r = 2m + e feeds output row m with tap row e and output
@@ -522,7 +823,37 @@ int launch_upfirdn2d(const float* x, float* y, const float* k, int planes, int i
   if (planes == 0) return HF_OK;
   const bool k4 = (kh == 4 && kw == 4);
   const bool sym = (up_x == up_y && down_x == down_y);
-  if (k4 && sym && up_x == 1 && down_x == 1 && planes <= 65535 && px0 >= 0 && py0 >= 0 && px1 >= 0 && py1 >= 0) {
+  const bool pads03 = px0 >= 0 && py0 >= 0 && px1 >= 0 && py1 >= 0 && px0 <= 3 && px1 <= 3 && py0 <= 3 && py1 <= 3;
+  // TMA-fed strip kernels (see upfirdn2d_k4_bulk_kernel): full-width rows, 16-byte aligned tensor, pads 0..3
+  const bool bulk_ok = k4 && sym && planes <= 65535 && in_w >= 64 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                       ((size_t)planes * in_h * in_w) % 4 == 0;
+  auto bulk_stage = [&](int CR) {
+    return (uint32_t)((((size_t)CR * in_w * 4 + 15) / 16 * 16 + 32 + 127) / 128 * 128);
+  };
+  auto bulk_go = [&](auto kern, int rows_per_cta, int CR, int S, auto... tail) {
+    const uint32_t stage = bulk_stage(CR);                 // <= 25 KB for the widths admitted below
+    static const void* opted[8] = {};                      // kernels whose dynamic-smem limit has been raised (6 exist)
+    const void* fn = reinterpret_cast<const void*>(kern);
+    int slot = 0;
+    while (slot < 8 && opted[slot] && opted[slot] != fn) ++slot;
+    if (slot == 8 || !opted[slot]) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (slot < 8) opted[slot] = fn;
+    }
+    dim3 grid(1, cdiv(up_x == 2 ? in_h : out_h, rows_per_cta), planes);
+    kern<<<grid, 256, S * stage, st>>>(x, y, k, in_h, in_w, tail..., stage);
+  };
+  if (bulk_ok && up_x == 1 && down_x == 1 && pads03 && out_w <= 1024 && in_w <= 1040) {
+    if (out_w <= 512) bulk_go(upfirdn2d_k4_bulk_kernel<1, 2, 64, 4, 3>, 64, 4, 3, out_h, out_w, px0, py0);
+    else bulk_go(upfirdn2d_k4_bulk_kernel<1, 4, 64, 4, 3>, 64, 4, 3, out_h, out_w, px0, py0);
+  } else if (bulk_ok && up_x == 1 && down_x == 2 && pads03 && out_w <= 1024 && in_w <= 1040) {
+    if (out_w <= 512) bulk_go(upfirdn2d_k4_bulk_kernel<2, 2, 32, 4, 3>, 32, 4, 3, out_h, out_w, px0, py0);
+    else bulk_go(upfirdn2d_k4_bulk_kernel<2, 4, 32, 4, 3>, 32, 4, 3, out_h, out_w, px0, py0);
+  } else if (bulk_ok && up_x == 2 && down_x == 1 && px0 == 2 && py0 == 2 && px1 == 1 && py1 == 1 && in_w <= 1024 &&
+             (reinterpret_cast<uintptr_t>(y) & 7) == 0) {
+    if (in_w <= 512) bulk_go(upfirdn2d_up2_k4_bulk_kernel<2, 32, 6, 3>, 32, 6, 3);
+    else bulk_go(upfirdn2d_up2_k4_bulk_kernel<4, 32, 6, 3>, 32, 6, 3);
+  } else if (k4 && sym && up_x == 1 && down_x == 1 && planes <= 65535 && px0 >= 0 && py0 >= 0 && px1 >= 0 && py1 >= 0) {
     constexpr int RS = 64;                                   // rows per warp strip (3 halo rows each)
     const int wx = out_w > 512 ? 8 : out_w > 256 ? 4 : out_w > 128 ? 2 : 1;   // warps side by side
     dim3 grid(cdiv(out_w, 128 * wx), cdiv(out_h, RS * (8 / wx)), planes);

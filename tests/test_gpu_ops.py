@@ -53,6 +53,61 @@ def test_upfirdn2d_vs_oracle(op, shape, up, down, pad):
     assert float((y.cpu() - ref).abs().max()) < TOL_FP32 * 4
 
 
+@pytest.mark.parametrize("shape,up,down,pad", [
+    # TMA bulk strips (full-width rows fetched with cp.async.bulk): up 1 = the blur after the up-conv
+    ((2, 2, 131, 257), 1, 1, (1, 1)),    # rows only 4-byte aligned
+    ((1, 4, 70, 129), 1, 1, (2, 1)),     # padding rows above, one padding column right
+    ((1, 4, 200, 1025), 1, 1, (1, 1)),   # the 1024-wide case (4 columns per thread), several strips
+    ((4, 1, 67, 1027), 1, 1, (0, 0)),    # no padding at all
+    ((1, 4, 66, 300), 1, 1, (3, 3)),     # widest padding, 2 columns per thread
+    ((1, 4, 9, 128), 1, 1, (0, 3)),      # a single short strip
+    # down 2 (Downsample / ConvLayer blur)
+    ((2, 2, 131, 257), 1, 2, (1, 1)),
+    ((1, 4, 70, 1024), 1, 2, (1, 1)),
+    ((1, 4, 66, 1039), 1, 2, (2, 3)),    # out_w = 521: 4 columns per thread
+    ((1, 4, 67, 300), 1, 2, (0, 0)),
+    ((1, 4, 9, 128), 1, 2, (3, 0)),
+    # up 2 (RGB-skip Upsample), pad (2,1)
+    ((2, 2, 37, 65), 2, 1, (2, 1)),
+    ((1, 4, 70, 512), 2, 1, (2, 1)),
+    ((1, 4, 35, 1024), 2, 1, (2, 1)),    # 4 columns per thread
+    ((1, 4, 3, 129), 2, 1, (2, 1)),
+    ((1, 4, 1, 64), 2, 1, (2, 1)),       # one input row
+])
+@pytest.mark.parametrize("separable", [True, False])
+def test_upfirdn2d_bulk_paths_vs_oracle(op, shape, up, down, pad, separable):
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(*shape, generator=g)
+    k = O.make_kernel([1, 3, 3, 1]) * (up ** 2) if separable else torch.randn(4, 4, generator=g)
+    ref = O.upfirdn2d_ref(x, k, up, down, pad)
+    y = op.upfirdn2d(x.cuda(), k.cuda(), up=up, down=down, pad=pad)
+    assert y.shape == ref.shape
+    assert float((y.cpu() - ref).abs().max()) < TOL_FP32 * 4
+    # the same call on a 4-byte-offset view takes the ring / register-window kernels instead: both paths must agree
+    buf = torch.empty(x.numel() + 1, device="cuda")
+    xv = buf[1:].view(shape)
+    xv.copy_(x)
+    y2 = op.upfirdn2d(xv, k.cuda(), up=up, down=down, pad=pad)
+    assert float((y2 - y).abs().max()) < 1e-5
+
+
+def test_upfirdn2d_blur_full_size_both_paths(op):
+    """The north_star blur shape [B*C, 1025, 1025] -> 1024^2 (model.py:252-263) at full size: TMA bulk path vs the
+    ring kernel on an unaligned view of the same data, plus the DC gain of the normalised FIR in the interior."""
+    k = (O.make_kernel([1, 3, 3, 1]) * 4).cuda()
+    x = torch.randn(1, 8, 1025, 1025, device="cuda")
+    y = op.upfirdn2d(x, k / 4, up=1, down=1, pad=(1, 1))
+    assert y.shape == (1, 8, 1024, 1024)
+    buf = torch.empty(x.numel() + 1, device="cuda")
+    xv = buf[1:].view(x.shape)
+    xv.copy_(x)
+    y2 = op.upfirdn2d(xv, k / 4, up=1, down=1, pad=(1, 1))
+    assert float((y2 - y).abs().max()) < 1e-5
+    ones = torch.ones(1, 4, 1025, 1025, device="cuda")
+    y1 = op.upfirdn2d(ones, k / 4, up=1, down=1, pad=(1, 1))
+    assert float((y1[:, :, 2:-2, 2:-2] - 1).abs().max()) < 1e-6
+
+
 def test_upfirdn2d_other_kernel_sizes(op):
     g = torch.Generator().manual_seed(6)
     x = torch.randn(2, 3, 12, 10, generator=g)
