@@ -2,6 +2,7 @@
 // demodulation tables, NCHW->NHWC modulate+cast pre-pass, RGB combine (+ up-FIR of the skip),
 // standalone ToRGB, weight packing.  All fp32 math; 16-bit only as storage for tensor-core operands.
 #include "hf_kernels.cuh"
+#include <type_traits>
 
 namespace hf {
 
@@ -383,89 +384,103 @@ __global__ void __launch_bounds__(256) upfirdn2d_k4_bulk_kernel(const float* __r
     if (in_img) live |= 1u << j;
     if (in_img && !inside) edge |= 1u << j;
   }
-  float acc[NACC][NC];
-#pragma unroll
-  for (int i = 0; i < NACC; ++i)
-#pragma unroll
-    for (int j = 0; j < NC; ++j) acc[i][j] = 0.f;
+  const bool any_edge = edge != 0;
+  float* dst_row = yp + (size_t)oy0 * out_w + t;                       // next output row to complete (they complete in order)
+  const uint32_t row_bytes = (uint32_t)in_w * 4u;
 
+  // The whole strip loop is instantiated once per FIR kind so that the separable test is not re-evaluated per row.
+  auto run = [&](auto sep_tag) {
+    constexpr bool SEP = decltype(sep_tag)::value;
+    float acc[NACC][NC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i)
+#pragma unroll
+      for (int j = 0; j < NC; ++j) acc[i][j] = 0.f;
 #pragma unroll 1
-  for (int c = 0; c < nchunks; ++c) {
-    const BulkSpan sp = bulk_span(c, CR, iy0, nrows, in_h, in_w, plane_off);
-    const int s = c % S;
-    if (sp.lo < sp.hi) mbar_wait(&full[s], (uint32_t)(c / S) & 1u);
-    const uint32_t stage_s = smem_s + (uint32_t)s * stage_bytes;
+    for (int c = 0; c < nchunks; ++c) {
+      const BulkSpan sp = bulk_span(c, CR, iy0, nrows, in_h, in_w, plane_off);
+      const int s = c % S;
+      if (sp.lo < sp.hi) mbar_wait(&full[s], (uint32_t)(c / S) & 1u);
+      // shared address of strip row c*CR (may lie before the span when that row is padding: never dereferenced then)
+      uint32_t row_s = smem_s + (uint32_t)s * stage_bytes +
+                       (uint32_t)(int32_t)((int64_t)((plane_off + (size_t)sp.lo * in_w) * 4 - sp.a0) +
+                                           (int64_t)(iy0 + c * CR - sp.lo) * (int64_t)row_bytes);
 #pragma unroll
-    for (int u8 = 0; u8 < CR; ++u8) {
-      const int r = c * CR + u8;
-      if (r < nrows) {                                                 // block-uniform
-        const int iy = iy0 + r;
-        const bool row_ok = iy >= sp.lo && iy < sp.hi;                 // block-uniform: padding rows add nothing
-        // DOWN 1: input row r feeds output rows r - a (tap row a), slot (r - a) & 3.  DOWN 2: r = 2m + e feeds output
-        // m (tap row e, slot cur) and m - 1 (tap row e + 2, slot prev).  Static because chunks start at multiples of 4.
-        const int u = u8 & 3, e = u8 & 1, cur = (u8 >> 1) & 1, prev = cur ^ 1;
-        if (row_ok) {
-          const uint32_t row_s = stage_s + (uint32_t)((plane_off + (size_t)iy * in_w) * 4 - sp.a0);
-          float v[NC][4];
+      for (int u8 = 0; u8 < CR; ++u8, row_s += row_bytes) {
+        const int r = c * CR + u8;
+        if (r < nrows) {                                               // block-uniform
+          const int iy = iy0 + r;
+          const bool row_ok = iy >= sp.lo && iy < sp.hi;               // block-uniform: padding rows add nothing
+          // DOWN 1: input row r feeds output rows r - a (tap row a), slot (r - a) & 3.  DOWN 2: r = 2m + e feeds
+          // output m (tap row e, slot cur) and m - 1 (tap row e + 2, slot prev).  Static: chunks start at multiples of 4.
+          const int u = u8 & 3, e = u8 & 1, cur = (u8 >> 1) & 1, prev = cur ^ 1;
+          if (row_ok) {
+            float v[NC][4];
 #pragma unroll
-          for (int j = 0; j < NC; ++j) {
-            if (edge & (1u << j)) {                                    // a padding column inside this window
-              const int ix = DOWN * (t + 256 * j) - px0;
-#pragma unroll
-              for (int b = 0; b < 4; ++b)
-                v[j][b] = (ix + b >= 0 && ix + b < in_w) ? lds_f32(row_s + (uint32_t)(ix + b) * 4u) : 0.f;
-            } else {
+            for (int j = 0; j < NC; ++j)
 #pragma unroll
               for (int b = 0; b < 4; ++b) v[j][b] = lds_f32(row_s + off[j] + 4u * b);
+            if (any_edge) {                                            // the few threads that own an edge column redo it
+#pragma unroll
+              for (int j = 0; j < NC; ++j)
+                if (edge & (1u << j)) {
+                  const int ix = DOWN * (t + 256 * j) - px0;
+#pragma unroll
+                  for (int b = 0; b < 4; ++b)
+                    v[j][b] = (ix + b >= 0 && ix + b < in_w) ? lds_f32(row_s + (uint32_t)(ix + b) * 4u) : 0.f;
+                }
             }
-          }
-          if (separable) {
+            if constexpr (SEP) {
 #pragma unroll
-            for (int j = 0; j < NC; ++j) {
-              float h = v[j][0] * kx[0];
+              for (int j = 0; j < NC; ++j) {
+                float h = v[j][0] * kx[0];
 #pragma unroll
-              for (int b = 1; b < 4; ++b) h = fmaf(v[j][b], kx[b], h);
-              if constexpr (DOWN == 1) {
-#pragma unroll
-                for (int a = 0; a < 4; ++a) acc[(u - a) & 3][j] = fmaf(h, ky[a], acc[(u - a) & 3][j]);
-              } else {
-                acc[cur][j] = fmaf(h, ky[e], acc[cur][j]);
-                acc[prev][j] = fmaf(h, ky[e + 2], acc[prev][j]);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < NC; ++j)
-#pragma unroll
-              for (int b = 0; b < 4; ++b) {
+                for (int b = 1; b < 4; ++b) h = fmaf(v[j][b], kx[b], h);
                 if constexpr (DOWN == 1) {
 #pragma unroll
-                  for (int a = 0; a < 4; ++a) acc[(u - a) & 3][j] = fmaf(v[j][b], kr[a * 4 + b], acc[(u - a) & 3][j]);
+                  for (int a = 0; a < 4; ++a) acc[(u - a) & 3][j] = fmaf(h, ky[a], acc[(u - a) & 3][j]);
                 } else {
-                  acc[cur][j] = fmaf(v[j][b], kr[e * 4 + b], acc[cur][j]);
-                  acc[prev][j] = fmaf(v[j][b], kr[(e + 2) * 4 + b], acc[prev][j]);
+                  acc[cur][j] = fmaf(h, ky[e], acc[cur][j]);
+                  acc[prev][j] = fmaf(h, ky[e + 2], acc[prev][j]);
                 }
               }
-          }
-        }
-        // the output row that is complete once this input row has been added (row counts bound it by nrows)
-        const int orow = DOWN == 1 ? r - 3 : (r >> 1) - 1;
-        const int slot = DOWN == 1 ? (u + 1) & 3 : prev;
-        if (DOWN == 1 || e == 1) {
-          if (orow >= 0) {
-            float* dst = yp + (size_t)(oy0 + orow) * out_w + t;
+            } else {
 #pragma unroll
-            for (int j = 0; j < NC; ++j)
-              if (live & (1u << j)) __stcs(dst + 256 * j, acc[slot][j]);
-          }
+              for (int j = 0; j < NC; ++j)
 #pragma unroll
-          for (int j = 0; j < NC; ++j) acc[slot][j] = 0.f;
+                for (int b = 0; b < 4; ++b) {
+                  if constexpr (DOWN == 1) {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+                      acc[(u - a) & 3][j] = fmaf(v[j][b], kr[a * 4 + b], acc[(u - a) & 3][j]);
+                  } else {
+                    acc[cur][j] = fmaf(v[j][b], kr[e * 4 + b], acc[cur][j]);
+                    acc[prev][j] = fmaf(v[j][b], kr[(e + 2) * 4 + b], acc[prev][j]);
+                  }
+                }
+            }
+          }
+          // the output row that is complete once this input row has been added (row counts bound it by nrows)
+          const int orow = DOWN == 1 ? r - 3 : (r >> 1) - 1;
+          const int slot = DOWN == 1 ? (u + 1) & 3 : prev;
+          if (DOWN == 1 || e == 1) {
+            if (orow >= 0) {
+#pragma unroll
+              for (int j = 0; j < NC; ++j)
+                if (live & (1u << j)) __stcs(dst_row + 256 * j, acc[slot][j]);
+              dst_row += out_w;
+            }
+#pragma unroll
+            for (int j = 0; j < NC; ++j) acc[slot][j] = 0.f;
+          }
         }
       }
+      __syncthreads();                                                 // every thread is done with stage s
+      if (t == 0 && c + S < nchunks) issue_chunk(c + S);
     }
-    __syncthreads();                                                   // every thread is done with stage s
-    if (t == 0 && c + S < nchunks) issue_chunk(c + S);
-  }
+  };
+  if (separable) run(std::true_type{});
+  else run(std::false_type{});
 }
 
 // up = 2, down = 1, 4x4 taps, pad (2,1) (the RGB-skip Upsample) with the same TMA-fed strips: a thread owns the input
@@ -518,6 +533,9 @@ __global__ void __launch_bounds__(256) upfirdn2d_up2_k4_bulk_kernel(const float*
     if (in_img) live |= 1u << j;
     if (in_img && !inside) edge |= 1u << j;
   }
+  const bool any_edge = edge != 0;
+  const uint32_t row_bytes = (uint32_t)in_w * 4u;
+  float* dst_row = yp + (size_t)(2 * y0) * out_w + 2 * t;             // output rows are produced in order
   float win[3][NC][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -530,35 +548,40 @@ __global__ void __launch_bounds__(256) upfirdn2d_up2_k4_bulk_kernel(const float*
     const BulkSpan sp = bulk_span(c, CR, iy0, nrows, in_h, in_w, plane_off);
     const int s = c % S;
     if (sp.lo < sp.hi) mbar_wait(&full[s], (uint32_t)(c / S) & 1u);
-    const uint32_t stage_s = smem_s + (uint32_t)s * stage_bytes;
+    uint32_t row_s = smem_s + (uint32_t)s * stage_bytes +
+                     (uint32_t)(int32_t)((int64_t)((plane_off + (size_t)sp.lo * in_w) * 4 - sp.a0) +
+                                         (int64_t)(iy0 + c * CR - sp.lo) * (int64_t)row_bytes);
 #pragma unroll
-    for (int u8 = 0; u8 < CR; ++u8) {
+    for (int u8 = 0; u8 < CR; ++u8, row_s += row_bytes) {
       const int r = c * CR + u8;
       if (r < nrows) {
         const int u = u8 % 3;                                          // strip row r lives in window slot r % 3 = u
         const int iy = iy0 + r;
         const bool row_ok = iy >= sp.lo && iy < sp.hi;
-        const uint32_t row_s = stage_s + (uint32_t)((plane_off + (size_t)(row_ok ? iy : sp.lo) * in_w) * 4 - sp.a0);
+        if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < NC; ++j) {
-          if (!row_ok) {
-#pragma unroll
-            for (int b = 0; b < 3; ++b) win[u][j][b] = 0.f;
-          } else if (edge & (1u << j)) {
-            const int ix = t + 256 * j - 1;
-#pragma unroll
-            for (int b = 0; b < 3; ++b)
-              win[u][j][b] = (ix + b >= 0 && ix + b < in_w) ? lds_f32(row_s + (uint32_t)(ix + b) * 4u) : 0.f;
-          } else {
+          for (int j = 0; j < NC; ++j)
 #pragma unroll
             for (int b = 0; b < 3; ++b) win[u][j][b] = lds_f32(row_s + off[j] + 4u * b);
+          if (any_edge) {
+#pragma unroll
+            for (int j = 0; j < NC; ++j)
+              if (edge & (1u << j)) {
+                const int ix = t + 256 * j - 1;
+#pragma unroll
+                for (int b = 0; b < 3; ++b)
+                  win[u][j][b] = (ix + b >= 0 && ix + b < in_w) ? lds_f32(row_s + (uint32_t)(ix + b) * 4u) : 0.f;
+              }
           }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NC; ++j)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) win[u][j][b] = 0.f;
         }
         if (r >= 2) {                                                  // rows yy-1, yy, yy+1 = strip rows r-2, r-1, r
-          const int yy = y0 + r - 2;
 #pragma unroll
           for (int py = 0; py < 2; ++py) {
-            float* dst = yp + (size_t)(2 * yy + py) * out_w + 2 * t;
 #pragma unroll
             for (int j = 0; j < NC; ++j) {
               float o[2];
@@ -572,8 +595,9 @@ __global__ void __launch_bounds__(256) upfirdn2d_up2_k4_bulk_kernel(const float*
                     sum = fmaf(win[(u + 1 + py + a) % 3][j][px + b], kr[(py + 2 * a) * 4 + px + 2 * b], sum);
                 o[px] = sum;
               }
-              if (live & (1u << j)) __stcs(reinterpret_cast<float2*>(dst + 512 * j), make_float2(o[0], o[1]));
+              if (live & (1u << j)) __stcs(reinterpret_cast<float2*>(dst_row + 512 * j), make_float2(o[0], o[1]));
             }
+            dst_row += out_w;
           }
         }
       }
