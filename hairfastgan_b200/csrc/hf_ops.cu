@@ -856,14 +856,8 @@ int launch_upfirdn2d(const float* x, float* y, const float* k, int planes, int i
   };
   auto bulk_go = [&](auto kern, int rows_per_cta, int CR, int S, auto... tail) {
     const uint32_t stage = bulk_stage(CR);                 // <= 25 KB for the widths admitted below
-    static const void* opted[8] = {};                      // kernels whose dynamic-smem limit has been raised (6 exist)
-    const void* fn = reinterpret_cast<const void*>(kern);
-    int slot = 0;
-    while (slot < 8 && opted[slot] && opted[slot] != fn) ++slot;
-    if (slot == 8 || !opted[slot]) {
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      if (slot < 8) opted[slot] = fn;
-    }
+    // per launch like the convolution kernels: the attribute is per device, a cache would have to be too
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     dim3 grid(1, cdiv(up_x == 2 ? in_h : out_h, rows_per_cta), planes);
     kern<<<grid, 256, S * stage, st>>>(x, y, k, in_h, in_w, tail..., stage);
   };
